@@ -1,0 +1,40 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def state():
+    """Seeded synthetic weights shared by oracle and engine (weights.make_state)."""
+    import torch
+    from voicefixer_main_b200.weights import make_state
+    torch.set_num_threads(os.cpu_count() or 1)
+    return make_state(1234)
+
+
+def load_golden(name):
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.fixture(scope="session")
+def golden_fingerprint_ok(state):
+    """The golden files were generated with make_state(1234); verify the local
+    generator reproduces the same weights before trusting any golden comparison."""
+    import numpy as np
+    from oracle.make_golden import state_fingerprint
+    fp = state_fingerprint(state)
+    ref = load_golden("stage_b_t101.npz")["fingerprint"]
+    assert np.allclose(fp, ref, rtol=1e-12), "synthetic weight generator drifted from the golden files"
+    return True

@@ -1,0 +1,63 @@
+"""Pin the restatement in oracle/vf_oracle.py against the reference's own modules,
+imported unmodified (build container only; skipped where /root/reference is absent)."""
+import pytest
+import torch
+
+from oracle import ref_import, vf_oracle as O
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref_model(state):
+    model, _ = ref_import.build_reference_model(state)
+    return model
+
+
+def test_mel_filterbank_bit_identical(ref_model):
+    fb = O.mel_filterbank()
+    assert torch.equal(ref_model.mel.fb, fb)
+    assert int((fb != 0).sum()) == 2018            # SURVEY.md 8(a) a5 probe
+
+
+def test_log_helpers_match_reference():
+    ref_import.install_shims()
+    from tools.pytorch.pytorch_util import from_log, to_log
+    x = torch.rand(3, 1, 7, 128) * 3
+    x[0, 0, 0, :4] = 0
+    assert torch.equal(to_log(x), O.to_log(x))
+    y = torch.randn(3, 1, 7, 128) * 4
+    assert torch.equal(from_log(y), O.from_log(y))
+    with pytest.raises(AssertionError):
+        O.to_log(-x - 1)
+    with pytest.raises(AssertionError):
+        to_log(-x - 1)
+
+
+def test_unet_restatement_matches_reference(ref_model, state):
+    g = torch.Generator().manual_seed(3)
+    for t in (64, 101, 130):                          # multiple of 64, the reference smoke shape, ragged
+        mel = 10 ** (torch.randn(2, 1, t, 128, generator=g) - 1)
+        with torch.no_grad():
+            ref = ref_model(mel)["mel"]
+            mine = O.generator_forward(state, mel)
+        assert ref.shape == mine.shape == (2, 1, t, 128)
+        assert float((ref - mine).abs().max()) < 2e-5
+
+
+def test_handler_restatement_matches_reference(ref_model, state):
+    wav = O.synth_clips(2, 30000, seed=9)
+    with torch.no_grad():
+        ref = ref_import.reference_handler_batch(ref_model, wav, seg_samples=12000)   # 3 segments, last ragged
+        mine = O.restore(state, wav, seg_samples=12000)
+    assert ref.shape == mine.shape == wav.shape
+    assert float((ref - mine).abs().max()) < 1e-5
+
+
+def test_trim_center_matches_reference():
+    ref_import.install_shims()
+    from tools.utils import trim_center
+    for le, lr in ((20, 14), (443646, 441000), (16, 16)):
+        est = torch.arange(float(le))[None, None]
+        ref = torch.zeros(1, 1, lr)
+        assert torch.equal(trim_center(est, ref)[0], O.trim_center(est, lr))
