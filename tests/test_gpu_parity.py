@@ -1,0 +1,193 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(libb200vf.so via ctypes); the oracle and the golden files are only the checker."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import vf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 1e-4      # north star: mel mask within 1e-4 (log10 mel, max abs)
+WAV_RMS_TOL = 1e-3  # north star: waveform within 1e-3 RMS
+
+
+@pytest.fixture(scope="module")
+def model(state):
+    from voicefixer_main_b200 import VoiceFixer
+    m = VoiceFixer().load_state_dict(state).eval().to("cuda:0")
+    yield m
+    m._engine().check_errors()
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM vs SIMT validation kernel
+GEMM_CASES = [
+    # n_img, rows, cin, cout, ntaps, dilation        (BN, BK) exercised
+    (2, 300, 32, 32, 9, 1),      # (32, 32)  SW64
+    (1, 128, 32, 64, 3, 1),      # (64, 32)
+    (1, 257, 32, 128, 1, 1),     # (128, 32)
+    (2, 200, 64, 32, 3, 1),      # (32, 64)  SW128
+    (1, 129, 64, 64, 9, 1),      # (64, 64)
+    (2, 500, 128, 128, 3, 27),   # (128, 64), dilated taps, OOB rows
+    (3, 40, 384, 384, 9, 2),     # tiny image, 3 N tiles, long K
+    (1, 1000, 64, 192, 2, 1),    # N = 192 -> BN 64
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+@pytest.mark.parametrize("terms", [3, 1])
+def test_gemm_tcgen05_matches_simt(model, case, terms):
+    diff, ref = model._engine().selftest_gemm(*case[:5], dilation=case[5], terms=terms)
+    model._engine().check_errors()
+    assert ref > 0.1
+    assert diff <= 2e-5 * ref, (case, terms, diff, ref)
+
+
+# ------------------------------------------------------------------ stage A
+@pytest.mark.parametrize("name", ["stage_a_n4410.npz", "stage_a_n30001.npz"])
+def test_frontend_matches_reference_golden(model, name):
+    g = load_golden(name)
+    wav = torch.from_numpy(g["wav"]).cuda()
+    sp, cos, sin = model.f_helper.wav_to_spectrogram_phase(wav[:, None, :])
+    mel = model.mel(sp.permute(0, 1, 3, 2)).permute(0, 1, 3, 2)
+    assert sp.shape == g["sp"].shape and mel.shape == g["mel"].shape
+    sp_ref, _, _ = O.wav_to_spectrogram_phase(torch.from_numpy(g["wav"])[:, None, :], exact=True)
+    scale = float(sp_ref.max())
+    # against the exact (fp64) transform: fp32 FFT rounding only
+    assert float((sp.cpu().double() - sp_ref).abs().max()) < 2e-6 * scale
+    # against the reference's own fp32 conv-DFT output (golden): its rounding is the larger one
+    assert float((sp.cpu() - torch.from_numpy(g["sp"])).abs().max()) < 5e-6 * scale
+    assert float((mel.cpu() - torch.from_numpy(g["mel"])).abs().max()) < 5e-6 * float(g["mel"].max())
+    assert float((cos ** 2 + sin ** 2 - 1).abs().max()) < 1e-3 or float(sp.min()) <= 1.1e-4
+
+
+def test_frontend_rejects_short_input(model):
+    from voicefixer_main_b200._lib import EngineError
+    with pytest.raises(EngineError):
+        model.pre(torch.zeros(1, 1, 1000, device="cuda"))
+
+
+# ------------------------------------------------------------------ stage B
+@pytest.mark.parametrize("name", ["stage_b_t101.npz", "stage_b_t1001.npz"])
+def test_unet_matches_reference_golden(model, name, golden_fingerprint_ok):
+    g = load_golden(name)
+    out = model(torch.from_numpy(g["mel_orig"]).cuda())["mel"].cpu()
+    ref = torch.from_numpy(g["log_mel"])
+    err = (out - ref).abs()
+    print(name, "log-mel max err", float(err.max()), "rms", float(err.pow(2).mean().sqrt()))
+    assert out.shape == ref.shape
+    assert float(err.max()) < MEL_TOL
+    lm = O.to_log(torch.from_numpy(g["mel_orig"]))
+    assert float((out[..., 127] - lm[..., 127]).abs().max()) < 1e-6      # last bin is a pass-through
+
+
+def test_unet_simt_validation_path_agrees(model, state):
+    g = load_golden("stage_b_t101.npz")
+    x = torch.from_numpy(g["mel_orig"])[:1].cuda()
+    tc = model(x)["mel"]
+    eng = model._engine()
+    eng.set_option("validate_simt", 1)
+    try:
+        simt = model(x)["mel"]
+    finally:
+        eng.set_option("validate_simt", 0)
+    assert float((tc - simt).abs().max()) < 2e-5
+    assert float((simt.cpu() - torch.from_numpy(g["log_mel"])[:1]).abs().max()) < MEL_TOL
+
+
+@pytest.mark.parametrize("t", [64, 130])
+def test_unet_ragged_lengths_vs_oracle(model, state, t):
+    gen = torch.Generator().manual_seed(t)
+    mel = 10 ** (torch.randn(3, 1, t, 128, generator=gen) - 1)
+    with torch.no_grad():
+        ref = O.generator_forward(state, mel)
+    out = model(mel.cuda())["mel"].cpu()
+    assert float((out - ref).abs().max()) < MEL_TOL
+
+
+def test_to_log_assertion_behaviour(model):
+    mel = torch.rand(1, 1, 64, 128, device="cuda")
+    mel[0, 0, 3, 5] = -0.5
+    with pytest.raises(AssertionError):
+        model(mel)
+    model(mel.abs())      # flag is cleared; the next call works
+
+
+# ------------------------------------------------------------------ stage C (oracle = restatement, parity unpinned)
+def test_vocoder_vs_oracle(model, state):
+    gen = torch.Generator().manual_seed(17)
+    mel = 10 ** (torch.randn(2, 1, 37, 128, generator=gen) * 0.7 - 1.5)
+    with torch.no_grad():
+        ref = O.vocoder_forward(state, mel)
+    out = model.vocoder(mel.cuda()).cpu()
+    assert out.shape == ref.shape == (2, 1, (37 + 1 + 4) * 441)
+    rms = float((out - ref).pow(2).mean().sqrt())
+    print("vocoder rms err", rms, "max", float((out - ref).abs().max()), "ref rms", float(ref.pow(2).mean().sqrt()))
+    assert rms < WAV_RMS_TOL * 0.1
+
+
+# ------------------------------------------------------------------ end to end
+def test_restore_matches_reference_golden_1s(model, golden_fingerprint_ok):
+    g = load_golden("e2e_1s.npz")
+    wav = torch.from_numpy(g["wav"])
+    out = model.restore(wav.cuda()).cpu()
+    eng = model._engine()
+    eng.check_errors()
+    _, log_mel = eng.restore_stages(*wav.shape)
+    mel_err = float((log_mel.cpu()[:, None] - torch.from_numpy(g["log_mel"])).abs().max())
+    rms = float((out - torch.from_numpy(g["out"])).pow(2).mean().sqrt())
+    print("e2e 1s: log-mel max err", mel_err, "wav rms err", rms)
+    assert out.shape == wav.shape
+    assert rms < WAV_RMS_TOL
+    assert mel_err < 5e-3      # includes the reference's own fp32 conv-DFT noise in quiet bins
+
+
+def test_restore_10s_golden_and_batch_invariance(model, golden_fingerprint_ok):
+    g = load_golden("e2e_10s.npz")
+    wav = torch.from_numpy(g["wav"])
+    other = O.synth_clips(2, wav.shape[1], seed=77)
+    batch = torch.cat([other[:1], wav, other[1:]]).cuda()
+    out = model.restore(batch)
+    model._engine().check_errors()
+    rms = float((out[1].cpu() - torch.from_numpy(g["out"])[0]).pow(2).mean().sqrt())
+    print("e2e 10s wav rms err", rms)
+    assert rms < WAV_RMS_TOL
+    single = model.restore(batch[1:2].contiguous())
+    assert torch.equal(single[0], out[1])         # clips are independent: batching must not change a bit
+    again = model.restore(batch)
+    assert torch.equal(again, out)                # deterministic
+
+
+def test_handler_protocol_drop_in(model, state):
+    """The exact call sequence of eval_gsr_voicefixer.py:51-72 on the mirror objects."""
+    wav = O.synth_clips(1, 22050, seed=5)
+    segment = wav[0]
+    inp = segment[None, None, ...].cuda()
+    sp, _, _ = model.f_helper.wav_to_spectrogram_phase(inp)
+    mel_noisy = model.mel(sp.permute(0, 1, 3, 2)).permute(0, 1, 3, 2)
+    out_model = model(mel_noisy)
+    denoised_mel = model._engine().from_log(out_model["mel"])
+    out = model.vocoder(denoised_mel)
+    if torch.max(torch.abs(out)) > 1.0:
+        out = out / torch.max(torch.abs(out))
+    out = O.trim_center(out, segment.shape[-1])
+    with torch.no_grad():
+        ref = O.restore(state, wav, exact_stft=True)
+    assert out.shape == (1, 1, 22050)
+    assert float((out[0].cpu() - ref).pow(2).mean().sqrt()) < WAV_RMS_TOL
+    fused = model.restore(wav.cuda())
+    assert float((fused.cpu() - out[0].cpu()).abs().max()) < 1e-5
+
+
+def test_host_entry_point_and_launch_count(model):
+    wav = O.synth_clips(2, 8820, seed=8)
+    pin_in, pin_out = wav.pin_memory(), torch.empty_like(wav).pin_memory()
+    eng = model._engine()
+    dev = model.restore(wav.cuda()).cpu()
+    n0 = eng.launch_count()
+    model.restore_host(pin_in, pin_out)
+    torch.cuda.synchronize()
+    assert eng.launch_count() - n0 > 100          # our kernels ran, not a library fallback
+    assert torch.equal(pin_out, dev)
+    assert eng.workspace_bytes(2, 8820) > 0

@@ -1,0 +1,254 @@
+// HBM-bound helper kernels around the GEMMs: first UNet layer (Cin = 1), 2x2 average pooling, log/exp
+// maps, vocoder conditioning, reflection padding, the Cout = 1 tail conv + tanh + peak, peak-normalise + trim.
+// All of them are one-pass, vectorised (16-byte accesses on the channel-innermost planes) and write the
+// fp16 hi/lo planes the next tcgen05 GEMM consumes, so no tensor is re-read for an elementwise step.
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace vf {
+
+__device__ __forceinline__ float lrelu(float a, float slope) { return a > 0.f ? a : a * slope; }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) unet_first_kernel(UnetFirstParams p) {
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)p.batch * p.Tp * 128;
+  if (pix >= total) return;
+  const int f = pix & 127;
+  const int t = (pix >> 7) % p.Tp;
+  const int b = (pix >> 7) / p.Tp;
+  float out_a[32], out_r[32];
+  if (f == 127) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { out_a[c] = 0.f; out_r[c] = 0.f; }
+  } else {
+    float a[9];
+    float xc = 0.f;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int tt = t + dh - 1, ff = f + dw - 1;
+        float v = 0.f;
+        if (tt >= 0 && tt < p.Tp && ff >= 0 && ff < 127) {
+          const float x = tt < p.T ? __ldg(p.logmel + ((size_t)b * p.T + tt) * 128 + ff) : 0.f;
+          if (dh == 1 && dw == 1) xc = x;
+          v = lrelu(fmaf(x, p.bn1_scale, p.bn1_shift), p.slope);
+        }
+        a[dh * 3 + dw] = v;
+      }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float y = 0.f;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) y = fmaf(a[j], __ldg(p.w1 + c * 9 + j), y);
+      out_a[c] = lrelu(fmaf(y, __ldg(p.bn2_scale + c), __ldg(p.bn2_shift + c)), p.slope);
+      out_r[c] = fmaf(xc, __ldg(p.w_sc + c), __ldg(p.b_sc + c));
+    }
+  }
+  float4* rp = reinterpret_cast<float4*>(p.sc_raw + pix * 32);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rp[i] = make_float4(out_r[4 * i], out_r[4 * i + 1], out_r[4 * i + 2], out_r[4 * i + 3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_store8(p.a2.hi, p.a2.lo, pix * 32 + 8 * i, out_a + 8 * i);
+}
+cudaError_t launch_unet_first(const UnetFirstParams& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.batch * p.Tp * 128;
+  unet_first_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_kernel(PoolParams p) {
+  const int cg = p.C / 8;
+  const int Ho = p.H / 2, Wpo = p.Wp / 2;
+  const size_t total = (size_t)p.batch * Ho * Wpo * cg;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % cg;
+  const size_t opix = idx / cg;
+  const int w = opix % Wpo;
+  const int h = (opix / Wpo) % Ho;
+  const int b = opix / ((size_t)Wpo * Ho);
+  float v[8], a[8];
+  if (w == Wpo - 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = 0.f; a[i] = 0.f; }
+  } else {
+    const float* base = p.in + (((size_t)b * p.H + 2 * h) * p.Wp + 2 * w) * p.C + g * 8;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float* src = base + ((size_t)(q >> 1) * p.Wp + (q & 1)) * p.C;
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      s[0] += x0.x; s[1] += x0.y; s[2] += x0.z; s[3] += x0.w;
+      s[4] += x1.x; s[5] += x1.y; s[6] += x1.z; s[7] += x1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = s[i] * 0.25f;
+      a[i] = v[i];
+      if (p.a_scale) a[i] = fmaf(a[i], __ldg(p.a_scale + g * 8 + i), __ldg(p.a_shift + g * 8 + i));
+      a[i] = lrelu(a[i], p.slope);
+      if (!(fabsf(a[i]) <= 65504.f) && p.err) atomicCAS(p.err, 0, ERR_FP16_OVERFLOW);
+    }
+  }
+  const size_t o = opix * p.C + g * 8;
+  if (p.out_raw) {
+    reinterpret_cast<float4*>(p.out_raw + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p.out_raw + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (p.out_r.hi) split_store8(p.out_r.hi, p.out_r.lo, o, v);
+  if (p.out_a.hi) split_store8(p.out_a.hi, p.out_a.lo, o, a);
+}
+cudaError_t launch_pool(const PoolParams& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.batch * (p.H / 2) * (p.Wp / 2) * (p.C / 8);
+  pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void to_log_kernel(const float* in, float* out, size_t n, int* neg_count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[i];
+  if (x < 0.f && neg_count) atomicAdd(neg_count, 1);
+  out[i] = log10f(fmaxf(x, 1e-8f));
+}
+__global__ void from_log_kernel(const float* in, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = exp10f(fminf(in[i], 5.f));
+}
+cudaError_t launch_to_log(const float* in, float* out, size_t n, int* neg_count, cudaStream_t stream) {
+  to_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in, out, n, neg_count);
+  return cudaGetLastError();
+}
+cudaError_t launch_from_log(const float* in, float* out, size_t n, cudaStream_t stream) {
+  from_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voc_condition_kernel(VocCondParams p) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // (b, tv, group of 8 mel bins)
+  const size_t total = (size_t)p.batch * p.Tv * 16;
+  if (idx >= total) return;
+  const int g = idx & 15;
+  const int tv = (idx >> 4) % p.Tv;
+  const int b = (idx >> 4) / p.Tv;
+  float c[8];
+  if (tv >= p.T) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = p.tail_value;
+  } else {
+    const float* src = p.mel + ((size_t)b * p.T + tv) * 128 + g * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float m = __ldg(src + i);
+      if (p.is_log) m = exp10f(fminf(m, 5.f));                            // from_log, pytorch_util.py:161-163
+      const float v = fabsf(m) / __ldg(p.weight + g * 8 + i);
+      const float s = 20.f * log10f(fmaxf(v, p.amp_floor)) - p.ref_db;
+      c[i] = fminf(fmaxf((s - p.min_db) / (-p.min_db), 0.f), 1.f);
+    }
+  }
+  split_store8(p.out.hi, p.out.lo, ((size_t)b * p.Tv + tv) * 128 + g * 8, c);
+}
+cudaError_t launch_voc_condition(const VocCondParams& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.batch * p.Tv * 16;
+  voc_condition_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void reflect_fill_kernel(PlanePtr pl, int batch, int L, int C, int pad) {
+  const int cg = C / 8;
+  const size_t total = (size_t)batch * 2 * pad * cg;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % cg;
+  const int j = (idx / cg) % (2 * pad);
+  const int b = idx / ((size_t)cg * 2 * pad);
+  int dst, src;
+  if (j < pad) { dst = j; src = 2 * pad - j; }
+  else { const int i = j - pad; dst = L + pad + i; src = L - 2 - i + pad; }
+  const size_t rows = (size_t)L + 2 * pad;
+  const size_t d = ((size_t)b * rows + dst) * C + g * 8, s = ((size_t)b * rows + src) * C + g * 8;
+  *reinterpret_cast<uint4*>(pl.hi + d) = *reinterpret_cast<const uint4*>(pl.hi + s);
+  *reinterpret_cast<uint4*>(pl.lo + d) = *reinterpret_cast<const uint4*>(pl.lo + s);
+}
+cudaError_t launch_reflect_fill(PlanePtr planes, int batch, int L, int C, int pad, cudaStream_t stream) {
+  const size_t total = (size_t)batch * 2 * pad * (C / 8);
+  reflect_fill_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(planes, batch, L, C, pad);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voc_tail_kernel(VocTailParams p) {
+  extern __shared__ float w_s[];                                          // [7][C]
+  for (int i = threadIdx.x; i < 7 * p.C; i += blockDim.x) w_s[i] = p.w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  float mag = 0.f;
+  if (t < p.L) {
+    float acc = p.bias;
+    const size_t rows = (size_t)p.L + 6;
+    for (int k = 0; k < 7; ++k) {
+      const size_t base = ((size_t)b * rows + t + k) * p.C;
+      for (int c = 0; c < p.C; c += 8) {
+        const uint4 hq = __ldg(reinterpret_cast<const uint4*>(p.in.hi + base + c));
+        const __half* h = reinterpret_cast<const __half*>(&hq);
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = __half2float(h[i]);
+        if (p.terms == 3) {
+          const uint4 lq = __ldg(reinterpret_cast<const uint4*>(p.in.lo + base + c));
+          const __half* l = reinterpret_cast<const __half*>(&lq);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] += __half2float(l[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(a[i], w_s[k * p.C + c + i], acc);
+      }
+    }
+    const float y = tanhf(acc);
+    p.wav[(size_t)b * p.L + t] = y;
+    mag = fabsf(y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, o));
+  __shared__ float wmax[8];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mag;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, wmax[i]);
+    atomicMax(p.peak_bits + b, __float_as_uint(m));
+  }
+}
+cudaError_t launch_voc_tail(const VocTailParams& p, cudaStream_t stream) {
+  dim3 grid((unsigned)((p.L + 255) / 256), p.batch);
+  voc_tail_kernel<<<grid, 256, 7 * p.C * sizeof(float), stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void finalize_kernel(FinalizeParams p) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= p.n) return;
+  const float peak = __uint_as_float(p.peak_bits[b]);
+  float v = p.wav[(size_t)b * p.L + p.skip + i];
+  if (peak > 1.0f) v = v / peak;
+  p.out[(size_t)b * p.out_ld + p.out_off + i] = v;
+}
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream) {
+  dim3 grid((unsigned)((p.n + 255) / 256), p.batch);
+  finalize_kernel<<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace vf

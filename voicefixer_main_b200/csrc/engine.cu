@@ -1,0 +1,1303 @@
+// Host side of libb200vf.so: context, weight packing, per-shape launch plans, and the C ABI (include/b200vf.h).
+//
+// A plan is the full, pre-resolved launch list for one (batch, frames) shape: every activation buffer is
+// allocated once, every TMA tensor map is encoded once, and running a stage is a loop of kernel launches on
+// the caller's stream - no allocation, no host synchronisation, no CPU arithmetic on the data path.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b200vf.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace vf {
+cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
+int gemm_tc_stage_bytes(int bn, int bk);
+cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
+}  // namespace vf
+
+using namespace vf;
+
+namespace {
+
+std::string g_create_error;
+
+struct HostT {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+struct GemmW {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0;
+};
+struct Affine {
+  float* scale = nullptr;
+  float* shift = nullptr;
+};
+struct Planes {
+  PlanePtr p{nullptr, nullptr};
+  int C = 0;
+  int img_rows = 0;   // allocated rows per image
+};
+struct ASrc {
+  Planes pl;
+  int rows;           // valid rows per image (TMA bound / SIMT bound)
+  int row0;           // first valid row inside the allocation (reflection slack), usually 0
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+enum OpKind { OP_GEMM, OP_FIRST, OP_POOL, OP_COND, OP_REFLECT, OP_TAIL, OP_FINALIZE, OP_MEMSET32 };
+
+struct Op {
+  OpKind kind;
+  int bn = 0, bk = 0;
+  GemmTcParams tc;
+  GemmSimtParams simt;
+  UnetFirstParams first;
+  PoolParams pool;
+  VocCondParams cond;
+  struct { PlanePtr pl; int batch, L, C, pad; } refl;
+  VocTailParams tail;
+  FinalizeParams fin;
+  struct { void* p; size_t bytes; } ms;
+};
+
+struct ConvBlockW {
+  GemmW conv1, conv2;     // conv2 carries the 1x1 shortcut as an extra K segment when present
+  Affine bn1, bn2;
+  bool has_sc = false;
+  int cin = 0, cout = 0;
+};
+
+struct Plan {
+  int batch = 0, T = 0;
+  long n_samples = 0;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  std::vector<Op> frontend, unet, vocoder, tail;
+  float* d_wav = nullptr;        // [B, N]   staged input (restore_host)
+  float* d_out = nullptr;        // [B, N]
+  float* d_mel = nullptr;        // [B, T, 128] linear mel
+  float* d_logmel_in = nullptr;  // [B, T, 128] log10 mel (UNet input)
+  float* d_logmel_out = nullptr; // [B, T, 128]
+  float* d_voc_wav = nullptr;    // [B, L]
+  unsigned int* d_peak = nullptr;
+  long L = 0;
+  // op slots patched per call
+  int fe_op = -1, cond_op = -1, fin_op = -1;
+};
+
+}  // namespace
+
+struct vf_ctx {
+  int device = 0;
+  vf_config cfg;
+  std::string err;
+  std::unordered_map<std::string, HostT> host_w;
+  std::vector<void*> allocs;
+  size_t weight_bytes = 0;
+  bool loaded = false;
+  EncodeTiledFn encode = nullptr;
+  int unet_terms = 3, voc_terms = 3, validate_simt = 0;
+  int64_t launches = 0;
+  int* d_err = nullptr;      // [0] device error code, [1] negative-input count
+  // tables
+  float* d_window = nullptr;
+  float2* d_tw1024 = nullptr;
+  float2* d_tw2048 = nullptr;
+  int *d_fb_f0 = nullptr, *d_fb_len = nullptr, *d_fb_ofs = nullptr;
+  float* d_fb_val = nullptr;
+  float* d_melw = nullptr;
+  // UNet weights
+  ConvBlockW enc[6][4], bott, dec[6][4], post;
+  GemmW dec_up[6];
+  Affine dec_bn1[6];
+  float first_bn1_scale = 1, first_bn1_shift = 0;
+  float* d_first_w1 = nullptr;
+  float* d_first_wsc = nullptr;
+  float* d_first_bsc = nullptr;
+  float* d_head_w = nullptr;
+  float head_b = 0;
+  // vocoder weights
+  std::vector<GemmW> voc_cond;
+  GemmW voc_stem;
+  std::vector<GemmW> voc_up;
+  std::vector<std::vector<GemmW>> voc_res_a, voc_res_b;
+  float* d_tail_w = nullptr;
+  float tail_b = 0;
+  int voc_last_c = 64;
+  std::map<std::pair<int, long>, std::unique_ptr<Plan>> plans;
+  bool timing = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+};
+
+namespace {
+
+int fail(vf_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, VF_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
+  } while (0)
+
+template <typename T>
+int dev_alloc(vf_ctx* ctx, std::vector<void*>& pool, size_t& acct, T** out, size_t count) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(ctx, VF_ECUDA, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  pool.push_back(p);
+  acct += bytes;
+  *out = static_cast<T*>(p);
+  return VF_OK;
+}
+template <typename T>
+int upload(vf_ctx* ctx, T** out, const std::vector<T>& h) {
+  int rc = dev_alloc(ctx, ctx->allocs, ctx->weight_bytes, out, h.size());
+  if (rc) return rc;
+  CK(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return VF_OK;
+}
+
+const HostT* find(vf_ctx* ctx, const std::string& k) {
+  auto it = ctx->host_w.find(k);
+  return it == ctx->host_w.end() ? nullptr : &it->second;
+}
+#define NEED(var, key)                                                                \
+  const HostT* var = find(ctx, key);                                                  \
+  if (!var) return fail(ctx, VF_ESTATE, "missing weight tensor '%s'", std::string(key).c_str());
+
+// fp32 matrix [N][K] -> device fp16 hi/lo pair (+ optional fp32 bias [N])
+int upload_gemm(vf_ctx* ctx, GemmW* w, const std::vector<float>& m, int N, int K, const std::vector<float>* bias) {
+  std::vector<__half> hi(m.size()), lo(m.size());
+  for (size_t i = 0; i < m.size(); ++i) {
+    hi[i] = __float2half_rn(m[i]);
+    lo[i] = __float2half_rn(m[i] - __half2float(hi[i]));
+  }
+  w->N = N;
+  w->K = K;
+  int rc = upload(ctx, &w->hi, hi);
+  if (rc) return rc;
+  rc = upload(ctx, &w->lo, lo);
+  if (rc) return rc;
+  if (bias) return upload(ctx, &w->bias, *bias);
+  return VF_OK;
+}
+
+// eval-mode BatchNorm2d -> a*x + b (modules.py:232-233, eps 1e-5)
+int fold_bn(vf_ctx* ctx, const std::string& p, std::vector<float>* scale, std::vector<float>* shift) {
+  NEED(w, p + ".weight");
+  NEED(b, p + ".bias");
+  NEED(m, p + ".running_mean");
+  NEED(v, p + ".running_var");
+  const size_t n = w->v.size();
+  scale->resize(n);
+  shift->resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const double a = (double)w->v[i] / std::sqrt((double)v->v[i] + 1e-5);
+    (*scale)[i] = (float)a;
+    (*shift)[i] = (float)((double)b->v[i] - (double)m->v[i] * a);
+  }
+  return VF_OK;
+}
+int upload_bn(vf_ctx* ctx, const std::string& p, Affine* a) {
+  std::vector<float> s, h;
+  int rc = fold_bn(ctx, p, &s, &h);
+  if (rc) return rc;
+  rc = upload(ctx, &a->scale, s);
+  if (rc) return rc;
+  return upload(ctx, &a->shift, h);
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Conv2d 3x3 [Cout][Cin][3][3] (+ optional 1x1 shortcut [Cout][Csc]) -> [Cout][9*Cin + pad64(Csc)]
+int pack_conv3x3(vf_ctx* ctx, GemmW* out, const HostT& w, const HostT* sc_w, const HostT* sc_b) {
+  const int cout = (int)w.shape[0], cin = (int)w.shape[1];
+  const int csc = sc_w ? (int)sc_w->shape[1] : 0;
+  const int cscp = sc_w ? round_up(csc, cin >= 64 ? 64 : 32) : 0;
+  const int K = 9 * cin + cscp;
+  std::vector<float> m((size_t)cout * K, 0.f);
+  for (int n = 0; n < cout; ++n) {
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < 9; ++t) m[(size_t)n * K + t * cin + c] = w.v[((size_t)n * cin + c) * 9 + t];
+    for (int c = 0; c < csc; ++c) m[(size_t)n * K + 9 * cin + c] = sc_w->v[(size_t)n * csc + c];
+  }
+  return upload_gemm(ctx, out, m, cout, K, sc_b ? &sc_b->v : nullptr);
+}
+
+// ConvTranspose2d k3 s2 [Cin][Cout][3][3] -> [4*Cout][4*Cin]; phase (ph,pw), tap (dh,dw) <-> kernel index
+// kh = ph + 2*dh (valid when <= 2, and dh = 0 for ph = 1).
+int pack_convT2d(vf_ctx* ctx, GemmW* out, const HostT& w) {
+  const int cin = (int)w.shape[0], cout = (int)w.shape[1];
+  const int N = 4 * cout, K = 4 * cin;
+  std::vector<float> m((size_t)N * K, 0.f);
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw)
+      for (int dh = 0; dh < 2; ++dh)
+        for (int dw = 0; dw < 2; ++dw) {
+          const int kh = ph + 2 * dh, kw = pw + 2 * dw;
+          if (kh > 2 || kw > 2) continue;
+          for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < cin; ++ci)
+              m[(size_t)((ph * 2 + pw) * cout + co) * K + (dh * 2 + dw) * cin + ci] =
+                  w.v[(((size_t)ci * cout + co) * 3 + kh) * 3 + kw];
+        }
+  return upload_gemm(ctx, out, m, N, K, nullptr);
+}
+
+// Conv1d [Cout][Cin][k] -> [Cout][k*Cin]
+int pack_conv1d(vf_ctx* ctx, GemmW* out, const HostT& w, const HostT& b) {
+  const int cout = (int)w.shape[0], cin = (int)w.shape[1], k = (int)w.shape[2];
+  const int K = k * cin;
+  std::vector<float> m((size_t)cout * K);
+  for (int n = 0; n < cout; ++n)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < k; ++t) m[(size_t)n * K + t * cin + c] = w.v[((size_t)n * cin + c) * k + t];
+  return upload_gemm(ctx, out, m, cout, K, &b.v);
+}
+
+// ConvTranspose1d [Cin][Cout][2s], stride s -> [s*Cout][2*Cin]: output phase r takes taps (q, k=r) and (q-1, k=r+s)
+int pack_convT1d(vf_ctx* ctx, GemmW* out, const HostT& w, const HostT& b, int s) {
+  const int cin = (int)w.shape[0], cout = (int)w.shape[1];
+  const int N = s * cout, K = 2 * cin;
+  std::vector<float> m((size_t)N * K), bias(N);
+  for (int r = 0; r < s; ++r)
+    for (int co = 0; co < cout; ++co) {
+      bias[r * cout + co] = b.v[co];
+      for (int j = 0; j < 2; ++j)
+        for (int ci = 0; ci < cin; ++ci)
+          m[(size_t)(r * cout + co) * K + j * cin + ci] = w.v[((size_t)ci * cout + co) * (2 * s) + r + j * s];
+    }
+  return upload_gemm(ctx, out, m, N, K, &bias);
+}
+
+int load_block(vf_ctx* ctx, const std::string& p, ConvBlockW* blk, bool skip_conv1) {
+  NEED(w1, p + ".conv1.weight");
+  NEED(w2, p + ".conv2.weight");
+  blk->cout = (int)w1->shape[0];
+  blk->cin = (int)w1->shape[1];
+  const HostT* scw = find(ctx, p + ".shortcut.weight");
+  const HostT* scb = find(ctx, p + ".shortcut.bias");
+  blk->has_sc = scw != nullptr;
+  if (blk->has_sc && !scb) return fail(ctx, VF_ESTATE, "missing weight tensor '%s.shortcut.bias'", p.c_str());
+  int rc = upload_bn(ctx, p + ".bn1", &blk->bn1);
+  if (rc) return rc;
+  rc = upload_bn(ctx, p + ".bn2", &blk->bn2);
+  if (rc) return rc;
+  if (!skip_conv1) {
+    rc = pack_conv3x3(ctx, &blk->conv1, *w1, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  if (skip_conv1) return pack_conv3x3(ctx, &blk->conv2, *w2, nullptr, nullptr);   // Cin = 1: shortcut precomputed
+  return pack_conv3x3(ctx, &blk->conv2, *w2, scw, scb);
+}
+
+const int ENC_C[6] = {32, 64, 128, 256, 384, 384};
+const int DEC_CIN[6] = {384, 384, 384, 256, 128, 64};
+const int DEC_COUT[6] = {384, 384, 256, 128, 64, 32};
+
+int build_tables(vf_ctx* ctx) {
+  const double PI = 3.14159265358979323846;
+  std::vector<float> win(2048);
+  for (int i = 0; i < 2048; ++i) win[i] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * i / 2048.0));
+  std::vector<float2> t1(1024), t2(1025);
+  for (int j = 0; j < 1024; ++j) t1[j] = make_float2((float)std::cos(2 * PI * j / 1024.0), (float)-std::sin(2 * PI * j / 1024.0));
+  for (int k = 0; k <= 1024; ++k) t2[k] = make_float2((float)std::cos(2 * PI * k / 2048.0), (float)-std::sin(2 * PI * k / 2048.0));
+  int rc = upload(ctx, &ctx->d_window, win);
+  if (rc) return rc;
+  rc = upload(ctx, &ctx->d_tw1024, t1);
+  if (rc) return rc;
+  rc = upload(ctx, &ctx->d_tw2048, t2);
+  if (rc) return rc;
+  std::vector<float> mw(128);
+  for (int i = 0; i < 128; ++i) mw[i] = (float)(ctx->cfg.voc_mel_weight_a * std::exp(ctx->cfg.voc_mel_weight_b * i));
+  return upload(ctx, &ctx->d_melw, mw);
+}
+
+int load_all(vf_ctx* ctx) {
+  const std::string U = "generator.analysis_module.";
+  // mel filterbank -> sparse rows (each triangular filter is one contiguous run of bins)
+  {
+    NEED(fb, "mel.fb");
+    if (fb->shape.size() != 2 || fb->shape[0] != 1025 || fb->shape[1] != 128)
+      return fail(ctx, VF_EINVAL, "mel.fb must be [1025,128]");
+    std::vector<int> f0(128), len(128), ofs(128);
+    std::vector<float> val;
+    for (int m = 0; m < 128; ++m) {
+      int lo = -1, hi = -1;
+      for (int f = 0; f < 1025; ++f)
+        if (fb->v[(size_t)f * 128 + m] != 0.f) { if (lo < 0) lo = f; hi = f; }
+      if (lo < 0) { lo = 0; hi = -1; }
+      f0[m] = lo; len[m] = hi - lo + 1; ofs[m] = (int)val.size();
+      for (int f = lo; f <= hi; ++f) val.push_back(fb->v[(size_t)f * 128 + m]);
+    }
+    if (val.empty()) val.push_back(0.f);
+    int rc = upload(ctx, &ctx->d_fb_f0, f0); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_fb_len, len); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_fb_ofs, ofs); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_fb_val, val); if (rc) return rc;
+  }
+  // UNet
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const std::string p = U + "encoder_block" + std::to_string(i + 1) + ".conv_block" + std::to_string(j + 1);
+      int rc = load_block(ctx, p, &ctx->enc[i][j], i == 0 && j == 0);
+      if (rc) return rc;
+    }
+  {
+    const std::string p = U + "encoder_block1.conv_block1";
+    std::vector<float> s, h;
+    int rc = fold_bn(ctx, p + ".bn1", &s, &h); if (rc) return rc;
+    ctx->first_bn1_scale = s[0]; ctx->first_bn1_shift = h[0];
+    NEED(w1, p + ".conv1.weight"); NEED(scw, p + ".shortcut.weight"); NEED(scb, p + ".shortcut.bias");
+    rc = upload(ctx, &ctx->d_first_w1, w1->v); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_first_wsc, scw->v); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_first_bsc, scb->v); if (rc) return rc;
+  }
+  int rc = load_block(ctx, U + "conv_block7", &ctx->bott, false); if (rc) return rc;
+  for (int i = 0; i < 6; ++i) {
+    const std::string p = U + "decoder_block" + std::to_string(i + 1);
+    NEED(up, p + ".conv1.weight");
+    rc = pack_convT2d(ctx, &ctx->dec_up[i], *up); if (rc) return rc;
+    rc = upload_bn(ctx, p + ".bn1", &ctx->dec_bn1[i]); if (rc) return rc;
+    for (int j = 0; j < 4; ++j) {
+      rc = load_block(ctx, p + ".conv_block" + std::to_string(j + 2), &ctx->dec[i][j], false);
+      if (rc) return rc;
+    }
+  }
+  rc = load_block(ctx, U + "after_conv_block1", &ctx->post, false); if (rc) return rc;
+  {
+    NEED(hw, U + "after_conv2.weight"); NEED(hb, U + "after_conv2.bias");
+    rc = upload(ctx, &ctx->d_head_w, hw->v); if (rc) return rc;
+    ctx->head_b = hb->v[0];
+  }
+  // vocoder
+  const vf_config& c = ctx->cfg;
+  ctx->voc_cond.resize(c.voc_cond_layers);
+  for (int i = 0; i < c.voc_cond_layers; ++i) {
+    NEED(w, "vocoder.condnet." + std::to_string(i) + ".weight"); NEED(b, "vocoder.condnet." + std::to_string(i) + ".bias");
+    rc = pack_conv1d(ctx, &ctx->voc_cond[i], *w, *b); if (rc) return rc;
+  }
+  {
+    NEED(w, "vocoder.stem.weight"); NEED(b, "vocoder.stem.bias");
+    rc = pack_conv1d(ctx, &ctx->voc_stem, *w, *b); if (rc) return rc;
+  }
+  ctx->voc_up.resize(c.voc_num_stages);
+  ctx->voc_res_a.assign(c.voc_num_stages, {});
+  ctx->voc_res_b.assign(c.voc_num_stages, {});
+  for (int s = 0; s < c.voc_num_stages; ++s) {
+    NEED(w, "vocoder.up." + std::to_string(s) + ".weight"); NEED(b, "vocoder.up." + std::to_string(s) + ".bias");
+    rc = pack_convT1d(ctx, &ctx->voc_up[s], *w, *b, c.voc_scales[s]); if (rc) return rc;
+    ctx->voc_res_a[s].resize(c.voc_depth[s]);
+    ctx->voc_res_b[s].resize(c.voc_depth[s]);
+    for (int i = 0; i < c.voc_depth[s]; ++i) {
+      const std::string p = "vocoder.res." + std::to_string(s) + "." + std::to_string(i);
+      NEED(wa, p + ".a.weight"); NEED(ba, p + ".a.bias"); NEED(wb, p + ".b.weight"); NEED(bb, p + ".b.bias");
+      rc = pack_conv1d(ctx, &ctx->voc_res_a[s][i], *wa, *ba); if (rc) return rc;
+      rc = pack_conv1d(ctx, &ctx->voc_res_b[s][i], *wb, *bb); if (rc) return rc;
+    }
+  }
+  {
+    NEED(w, "vocoder.tail.weight"); NEED(b, "vocoder.tail.bias");
+    const int cl = (int)w->shape[1], k = (int)w->shape[2];
+    if (k != 7) return fail(ctx, VF_EINVAL, "vocoder tail kernel must be 7");
+    std::vector<float> t((size_t)7 * cl);
+    for (int cch = 0; cch < cl; ++cch)
+      for (int kk = 0; kk < 7; ++kk) t[(size_t)kk * cl + cch] = w->v[(size_t)cch * 7 + kk];
+    rc = upload(ctx, &ctx->d_tail_w, t); if (rc) return rc;
+    ctx->tail_b = b->v[0];
+    ctx->voc_last_c = cl;
+  }
+  return VF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ plans
+struct Builder {
+  vf_ctx* ctx;
+  Plan* plan;
+  int rc = VF_OK;
+
+  template <typename T>
+  T* alloc(size_t count) {
+    T* p = nullptr;
+    if (rc) return nullptr;
+    rc = dev_alloc(ctx, plan->allocs, plan->bytes, &p, count);
+    return p;
+  }
+  Planes planes(size_t n_img, int img_rows, int C) {
+    Planes pl;
+    pl.C = C;
+    pl.img_rows = img_rows;
+    const size_t cnt = n_img * (size_t)img_rows * C;
+    pl.p.hi = alloc<__half>(cnt);
+    pl.p.lo = alloc<__half>(cnt);
+    return pl;
+  }
+
+  int make_map3(CUtensorMap* m, const __half* base, int C, int rows, int img_rows, int n_img, int box_c, bool sw128) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_img};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)img_rows * C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)GEMM_BM, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(A: C=%d rows=%d img_rows=%d n=%d box=%d) -> %d", C, rows, img_rows, n_img, box_c, (int)r);
+    return VF_OK;
+  }
+  int make_map2(CUtensorMap* m, const __half* base, int K, int N, int box_k, int box_n, bool sw128) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_n};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(B: K=%d N=%d box=%dx%d) -> %d", K, N, box_k, box_n, (int)r);
+    return VF_OK;
+  }
+
+  // taps: nch = real channel count; k segments are laid out back to back, each padded to BK.
+  void gemm(std::vector<Op>& ops, const GemmW& W, const ASrc& s0, const ASrc* s1, std::vector<GemmTap> taps,
+            GemmEpilogue epi, int n_img, int terms) {
+    if (rc) return;
+    Op op;
+    op.kind = OP_GEMM;
+    int bk = 64;
+    for (auto& t : taps)
+      if (t.nch % 64) bk = 32;
+    // a short tail segment (the 32-channel shortcut of a 64-channel conv) may be zero-padded to BK = 64 when
+    // the source has exactly that many channels: the TMA box then runs out of bounds and is zero-filled.
+    if (bk == 32) {
+      bool main64 = true, padok = true;
+      for (auto& t : taps) {
+        const ASrc& s = t.src ? *s1 : s0;
+        if (t.nch % 64) {
+          if (t.nch % 32 || t.c_off + t.nch != s.pl.C) padok = false;
+          if (&t != &taps.back()) main64 = false;
+        }
+      }
+      if (main64 && padok && taps.size() > 1) bk = 64;
+    }
+    const int N = W.N;
+    const int bn = (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
+    if (N % 32) { rc = fail(ctx, VF_EINVAL, "GEMM N=%d not a multiple of 32", N); return; }
+    int k = 0;
+    for (auto& t : taps) {
+      t.k_off = k;
+      const int padded = round_up(t.nch, bk);
+      k += padded;
+      if (ctx->validate_simt == 0) t.nch = padded;
+    }
+    if (k != W.K) { rc = fail(ctx, VF_EINVAL, "GEMM K mismatch: taps cover %d, packed weight has %d", k, W.K); return; }
+    GemmProblem pr;
+    memset(&pr, 0, sizeof pr);
+    pr.n_img = n_img;
+    pr.m_tiles = (epi.rows_in + GEMM_BM - 1) / GEMM_BM;
+    pr.N = N;
+    pr.ntaps = (int)taps.size();
+    pr.terms = terms;
+    if (pr.ntaps > GEMM_MAX_TAPS) { rc = fail(ctx, VF_EINVAL, "too many taps"); return; }
+    for (int i = 0; i < pr.ntaps; ++i) pr.taps[i] = taps[i];
+    epi.err = ctx->d_err;
+    pr.epi = epi;
+    op.bn = bn;
+    op.bk = bk;
+    if (ctx->validate_simt) {
+      GemmSimtParams& sp = op.simt;
+      memset(&sp, 0, sizeof sp);
+      const ASrc* srcs[2] = {&s0, s1};
+      for (int i = 0; i < 2; ++i) {
+        if (!srcs[i]) continue;
+        const size_t off = (size_t)srcs[i]->row0 * srcs[i]->pl.C;
+        sp.a_hi[i] = srcs[i]->pl.p.hi + off;
+        sp.a_lo[i] = srcs[i]->pl.p.lo + off;
+        sp.a_ld[i] = srcs[i]->pl.C;
+        sp.a_rows[i] = srcs[i]->rows;
+        sp.a_img_rows[i] = srcs[i]->pl.img_rows;
+      }
+      sp.b_hi = W.hi; sp.b_lo = W.lo; sp.ktot = W.K;
+      sp.prob = pr;
+    } else {
+      GemmTcParams& tp = op.tc;
+      memset(&tp, 0, sizeof tp);
+      const ASrc* srcs[2] = {&s0, s1 ? s1 : &s0};
+      for (int i = 0; i < 2 && !rc; ++i) {
+        const size_t off = (size_t)srcs[i]->row0 * srcs[i]->pl.C;
+        rc = make_map3(&tp.a_hi[i], srcs[i]->pl.p.hi + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64);
+        if (!rc) rc = make_map3(&tp.a_lo[i], srcs[i]->pl.p.lo + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64);
+      }
+      if (!rc) rc = make_map2(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
+      if (!rc) rc = make_map2(&tp.b_lo, W.lo, W.K, N, bk, bn, bk == 64);
+      const int stage = gemm_tc_stage_bytes(bn, bk);
+      int total_chunks = 0;
+      for (auto& t : taps) total_chunks += t.nch / bk;
+      int stages = std::min(bn == 128 ? 3 : 4, std::max(2, total_chunks));
+      while (stages > 2 && (size_t)stages * stage > 200 * 1024) --stages;
+      tp.stages = stages;
+      tp.prob = pr;
+    }
+    ops.push_back(op);
+  }
+};
+
+GemmEpilogue epi_plain(int rows_in, int Wp, int cout, int out_img_rows) {
+  GemmEpilogue e;
+  memset(&e, 0, sizeof e);
+  e.map = MAP_PLAIN;
+  e.rows_in = rows_in;
+  e.Wp = Wp;
+  e.cout = cout;
+  e.out_img_rows = out_img_rows;
+  e.out_rows_valid = out_img_rows;
+  return e;
+}
+void set_out_a(GemmEpilogue& e, const Planes& pl, int c_off, const float* scale, const float* shift, int act, float slope) {
+  e.out_a = OutPlane{pl.p.hi, pl.p.lo, pl.C, c_off};
+  e.a_scale = scale;
+  e.a_shift = shift;
+  e.act = act;
+  e.slope = slope;
+}
+std::vector<GemmTap> taps3x3(int Wp, int cin) {
+  std::vector<GemmTap> t;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) t.push_back(GemmTap{(kh - 1) * Wp + (kw - 1), 0, 0, 0, cin});
+  return t;
+}
+
+struct Level {
+  int H, Wp, C, rows;
+  float* raw[2];
+  Planes aX, aT, cat_r, cat_a, P_r, P_a;   // P_* : pooled output of this level (input of the next)
+  float* P_raw = nullptr;
+};
+
+int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
+  const int B = plan->batch, T = plan->T;
+  const int Tp = (T + 63) / 64 * 64;
+  std::vector<Op>& ops = plan->unet;
+  const int terms = ctx->unet_terms;
+  const float S = 0.01f;   // LeakyReLU slope, modules.py:265-266
+  Level lv[7];
+  for (int l = 0; l < 7; ++l) {
+    Level& L = lv[l];
+    L.H = Tp >> l; L.Wp = 128 >> l; L.C = l < 6 ? ENC_C[l] : 384; L.rows = L.H * L.Wp;
+    L.raw[0] = b.alloc<float>((size_t)B * L.rows * L.C);
+    L.raw[1] = b.alloc<float>((size_t)B * L.rows * L.C);
+    L.aX = b.planes(B, L.rows, L.C);
+    L.aT = b.planes(B, L.rows, L.C);
+    if (l < 6) {
+      L.cat_r = b.planes(B, L.rows, 2 * L.C);
+      L.cat_a = b.planes(B, L.rows, 2 * L.C);
+      L.P_r = b.planes(B, L.rows / 4, L.C);
+      L.P_a = b.planes(B, L.rows / 4, L.C);
+      if (l == 5) L.P_raw = b.alloc<float>((size_t)B * (L.rows / 4) * L.C);
+    }
+  }
+  if (b.rc) return b.rc;
+
+  // conv1 of a block: A -> aT with the block's bn2 + LeakyReLU
+  auto conv1 = [&](const ConvBlockW& w, Level& L, const Planes& in) {
+    GemmEpilogue e = epi_plain(L.rows, L.Wp, w.cout, L.rows);
+    set_out_a(e, L.aT, 0, w.bn2.scale, w.bn2.shift, ACT_LRELU, S);
+    b.gemm(ops, w.conv1, ASrc{in, L.rows, 0}, nullptr, taps3x3(L.Wp, w.cin), e, B, terms);
+  };
+  // conv2 of a block: aT (+ 1x1 shortcut of sc_src) (+ residual) -> outputs set by the caller
+  auto conv2 = [&](const ConvBlockW& w, Level& L, const Planes* sc_src, const float* resid, GemmEpilogue e) {
+    std::vector<GemmTap> taps = taps3x3(L.Wp, w.cout);
+    ASrc s1;
+    if (sc_src) {
+      taps.push_back(GemmTap{0, 1, 0, 0, sc_src->C});
+      s1 = ASrc{*sc_src, L.rows, 0};
+      e.bias = w.conv2.bias;
+    }
+    e.resid = resid;
+    e.resid_ld = w.cout;
+    b.gemm(ops, w.conv2, ASrc{L.aT, L.rows, 0}, sc_src ? &s1 : nullptr, taps, e, B, terms);
+  };
+
+  // ---------------- encoder
+  for (int l = 0; l < 6; ++l) {
+    Level& L = lv[l];
+    int cur = 0;   // raw[cur] holds the block input
+    for (int j = 0; j < 4; ++j) {
+      const ConvBlockW& w = ctx->enc[l][j];
+      const float* resid = nullptr;
+      const Planes* sc = nullptr;
+      if (j == 0 && l == 0) {
+        Op op; op.kind = OP_FIRST;
+        UnetFirstParams& f = op.first;
+        memset(&f, 0, sizeof f);
+        f.logmel = plan->d_logmel_in; f.batch = B; f.T = T; f.Tp = Tp;
+        f.bn1_scale = ctx->first_bn1_scale; f.bn1_shift = ctx->first_bn1_shift;
+        f.w1 = ctx->d_first_w1; f.bn2_scale = w.bn2.scale; f.bn2_shift = w.bn2.shift;
+        f.w_sc = ctx->d_first_wsc; f.b_sc = ctx->d_first_bsc; f.slope = S;
+        f.a2 = L.aT.p; f.sc_raw = L.raw[0]; f.err = ctx->d_err;
+        ops.push_back(op);
+        resid = L.raw[0];      // precomputed shortcut(x) acts as the residual
+        cur = 0;
+      } else if (j == 0) {
+        conv1(w, L, lv[l - 1].P_a);
+        sc = &lv[l - 1].P_r;
+        cur = 1;               // output goes to raw[0]
+      } else {
+        conv1(w, L, L.aX);
+        resid = L.raw[cur];
+      }
+      GemmEpilogue e = epi_plain(L.rows, L.Wp, w.cout, L.rows);
+      const int dst = (j == 0 && l > 0) ? 0 : 1 - cur;
+      e.out_raw = L.raw[dst];
+      e.raw_ld = L.C;
+      if (j < 3) {
+        const ConvBlockW& nx = ctx->enc[l][j + 1];
+        set_out_a(e, L.aX, 0, nx.bn1.scale, nx.bn1.shift, ACT_LRELU, S);
+      } else {
+        // skip connection: raw and activated halves of the decoder's concat buffer (modules.py:215)
+        const ConvBlockW& dblk = ctx->dec[5 - l][0];
+        e.out_r = OutPlane{L.cat_r.p.hi, L.cat_r.p.lo, 2 * L.C, L.C};
+        set_out_a(e, L.cat_a, L.C, dblk.bn1.scale + L.C, dblk.bn1.shift + L.C, ACT_LRELU, S);
+      }
+      conv2(w, L, sc, resid, e);
+      cur = dst;
+    }
+    // avg_pool2d(2,2) -> next stage's (or the bottleneck's) bn1 + LeakyReLU
+    Op op; op.kind = OP_POOL;
+    PoolParams& p = op.pool;
+    memset(&p, 0, sizeof p);
+    const ConvBlockW& nx = l < 5 ? ctx->enc[l + 1][0] : ctx->bott;
+    p.in = L.raw[cur]; p.batch = B; p.H = L.H; p.Wp = L.Wp; p.C = L.C;
+    p.out_r = L.P_r.p; p.out_a = L.P_a.p; p.out_raw = L.P_raw;
+    p.a_scale = nx.bn1.scale; p.a_shift = nx.bn1.shift; p.slope = S; p.err = ctx->d_err;
+    ops.push_back(op);
+  }
+  // ---------------- bottleneck (conv_block7, identity shortcut) -> decoder_block1.bn1 + ReLU
+  {
+    Level& L = lv[6];
+    conv1(ctx->bott, L, lv[5].P_a);
+    GemmEpilogue e = epi_plain(L.rows, L.Wp, 384, L.rows);
+    set_out_a(e, L.aX, 0, ctx->dec_bn1[0].scale, ctx->dec_bn1[0].shift, ACT_LRELU, 0.f);
+    conv2(ctx->bott, L, nullptr, lv[5].P_raw, e);
+  }
+  // ---------------- decoder
+  for (int k = 0; k < 6; ++k) {
+    Level& L = lv[5 - k];
+    Level& Lin = lv[6 - k];
+    const int cin = DEC_CIN[k], cout = DEC_COUT[k];
+    {   // ConvTranspose2d k3 s2 + prune + concat placement (modules.py:213-215)
+      GemmEpilogue e;
+      memset(&e, 0, sizeof e);
+      e.map = MAP_CONVT2D; e.rows_in = Lin.rows; e.Wp = Lin.Wp; e.cout = cout; e.out_img_rows = L.rows;
+      e.out_rows_valid = L.rows;
+      const ConvBlockW& blk = ctx->dec[k][0];
+      e.out_r = OutPlane{L.cat_r.p.hi, L.cat_r.p.lo, 2 * L.C, 0};
+      set_out_a(e, L.cat_a, 0, blk.bn1.scale, blk.bn1.shift, ACT_LRELU, S);
+      std::vector<GemmTap> taps;
+      for (int dh = 0; dh < 2; ++dh)
+        for (int dw = 0; dw < 2; ++dw) taps.push_back(GemmTap{-(dh * Lin.Wp + dw), 0, 0, 0, cin});
+      b.gemm(ops, ctx->dec_up[k], ASrc{Lin.aX, Lin.rows, 0}, nullptr, taps, e, B, terms);
+    }
+    int cur = 0;
+    for (int j = 0; j < 4; ++j) {
+      const ConvBlockW& w = ctx->dec[k][j];
+      const float* resid = nullptr;
+      const Planes* sc = nullptr;
+      if (j == 0) { conv1(w, L, L.cat_a); sc = &L.cat_r; }
+      else { conv1(w, L, L.aX); resid = L.raw[cur]; }
+      GemmEpilogue e = epi_plain(L.rows, L.Wp, w.cout, L.rows);
+      const int dst = j == 0 ? 0 : 1 - cur;
+      if (j < 3) {
+        const ConvBlockW& nx = ctx->dec[k][j + 1];
+        e.out_raw = L.raw[dst]; e.raw_ld = L.C;
+        set_out_a(e, L.aX, 0, nx.bn1.scale, nx.bn1.shift, ACT_LRELU, S);
+      } else if (k < 5) {
+        set_out_a(e, L.aX, 0, ctx->dec_bn1[k + 1].scale, ctx->dec_bn1[k + 1].shift, ACT_LRELU, 0.f);   // ReLU, modules.py:213
+      } else {
+        e.out_raw = L.raw[dst]; e.raw_ld = L.C;
+        set_out_a(e, L.aX, 0, ctx->post.bn1.scale, ctx->post.bn1.shift, ACT_LRELU, S);
+      }
+      conv2(w, L, sc, resid, e);
+      cur = dst;
+    }
+    if (k == 5) {   // after_conv_block1 + after_conv2 head + log-mel residual
+      conv1(ctx->post, L, L.aX);
+      GemmEpilogue e = epi_plain(L.rows, L.Wp, 32, L.rows);
+      e.head_w = ctx->d_head_w; e.head_b = ctx->head_b;
+      e.head_in = plan->d_logmel_in; e.head_out = plan->d_logmel_out; e.head_T = T;
+      conv2(ctx->post, L, nullptr, L.raw[cur], e);
+    }
+  }
+  return b.rc;
+}
+
+int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
+  const vf_config& c = ctx->cfg;
+  const int B = plan->batch, T = plan->T;
+  const int Tv = T + T % 2 + c.voc_tail_base;
+  const int terms = ctx->voc_terms;
+  std::vector<Op>& ops = plan->vocoder;
+  const int CC = c.voc_cond_channels;
+
+  Planes cond = b.planes(B, Tv, 128);
+  Planes c0 = b.planes(B, Tv, CC), c1 = b.planes(B, Tv, CC);
+  Planes cpad = b.planes(B, Tv + 6, CC);
+  Planes stem = b.planes(B, Tv, c.voc_channels);
+  if (b.rc) return b.rc;
+  {
+    Op op; op.kind = OP_COND;
+    VocCondParams& p = op.cond;
+    memset(&p, 0, sizeof p);
+    p.mel = plan->d_logmel_out; p.is_log = 1; p.batch = B; p.T = T; p.Tv = Tv; p.weight = ctx->d_melw;
+    p.amp_floor = c.voc_amp_floor; p.ref_db = c.voc_ref_db; p.min_db = c.voc_min_db; p.tail_value = c.voc_tail_value;
+    p.out = cond.p;
+    plan->cond_op = (int)ops.size();
+    ops.push_back(op);
+  }
+  auto taps1d = [](int k, int dil, int cin, bool centered) {
+    std::vector<GemmTap> t;
+    for (int i = 0; i < k; ++i) t.push_back(GemmTap{centered ? (i - (k - 1) / 2) * dil : i, 0, 0, 0, cin});
+    return t;
+  };
+  Planes cur = cond;
+  for (int i = 0; i < c.voc_cond_layers; ++i) {
+    const bool last = i == c.voc_cond_layers - 1;
+    Planes dst = last ? cpad : (i % 2 ? c1 : c0);
+    GemmEpilogue e = epi_plain(Tv, 0, CC, dst.img_rows);
+    e.out_row0 = last ? 3 : 0;
+    e.bias = ctx->voc_cond[i].bias;
+    set_out_a(e, dst, 0, nullptr, nullptr, ACT_ELU, 0.f);
+    b.gemm(ops, ctx->voc_cond[i], ASrc{cur, Tv, 0}, nullptr, taps1d(3, 1, cur.C, true), e, B, terms);
+    cur = dst;
+  }
+  { Op op; op.kind = OP_REFLECT; op.refl.pl = cpad.p; op.refl.batch = B; op.refl.L = Tv; op.refl.C = CC; op.refl.pad = 3; ops.push_back(op); }
+  {
+    GemmEpilogue e = epi_plain(Tv, 0, c.voc_channels, Tv);
+    e.bias = ctx->voc_stem.bias;
+    set_out_a(e, stem, 0, nullptr, nullptr, ACT_LRELU, c.voc_stage_slope);
+    b.gemm(ops, ctx->voc_stem, ASrc{cpad, Tv + 6, 0}, nullptr, taps1d(7, 1, CC, false), e, B, terms);
+  }
+  Planes prev = stem;
+  long Lprev = Tv;
+  int cin = c.voc_channels;
+  for (int s = 0; s < c.voc_num_stages; ++s) {
+    const int sc = c.voc_scales[s], cout = cin / 2;
+    const long L = Lprev * sc;
+    const bool last_stage = s == c.voc_num_stages - 1;
+    float* xr[2] = {b.alloc<float>((size_t)B * L * cout), b.alloc<float>((size_t)B * L * cout)};
+    Planes xa = b.planes(B, (int)L, cout), ha = b.planes(B, (int)L, cout);
+    Planes tail_in;
+    if (last_stage) tail_in = b.planes(B, (int)L + 6, cout);
+    if (b.rc) return b.rc;
+    {   // ConvTranspose1d: rows q = 0..Lprev produce s phases each
+      GemmEpilogue e;
+      memset(&e, 0, sizeof e);
+      e.map = MAP_CONVT1D; e.rows_in = (int)Lprev + 1; e.cout = cout; e.out_img_rows = (int)L; e.out_rows_valid = (int)L;
+      e.ct_stride = sc; e.ct_pad = sc / 2 + sc % 2;
+      e.bias = ctx->voc_up[s].bias;
+      e.out_raw = xr[0]; e.raw_ld = cout;
+      set_out_a(e, xa, 0, nullptr, nullptr, ACT_LRELU, c.voc_res_slope);
+      std::vector<GemmTap> taps = {GemmTap{0, 0, 0, 0, cin}, GemmTap{-1, 0, 0, 0, cin}};
+      b.gemm(ops, ctx->voc_up[s], ASrc{prev, (int)Lprev, 0}, nullptr, taps, e, B, terms);
+    }
+    int curx = 0;
+    for (int i = 0; i < c.voc_depth[s]; ++i) {
+      int dil = 1;
+      for (int q = 0; q < i % 10; ++q) dil *= 3;
+      const bool last = i == c.voc_depth[s] - 1;
+      {
+        GemmEpilogue e = epi_plain((int)L, 0, cout, (int)L);
+        e.bias = ctx->voc_res_a[s][i].bias;
+        set_out_a(e, ha, 0, nullptr, nullptr, ACT_LRELU, c.voc_res_slope);
+        b.gemm(ops, ctx->voc_res_a[s][i], ASrc{xa, (int)L, 0}, nullptr, taps1d(3, dil, cout, true), e, B, terms);
+      }
+      {
+        Planes dst = (last && last_stage) ? tail_in : xa;
+        GemmEpilogue e = epi_plain((int)L, 0, cout, dst.img_rows);
+        e.out_row0 = (last && last_stage) ? 3 : 0;
+        e.bias = ctx->voc_res_b[s][i].bias;
+        e.resid = xr[curx]; e.resid_ld = cout;
+        if (!last) { e.out_raw = xr[1 - curx]; e.raw_ld = cout; }
+        set_out_a(e, dst, 0, nullptr, nullptr, ACT_LRELU, last ? c.voc_stage_slope : c.voc_res_slope);
+        b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, nullptr, taps1d(3, 1, cout, true), e, B, terms);
+        curx = 1 - curx;
+      }
+    }
+    if (last_stage) {
+      { Op op; op.kind = OP_REFLECT; op.refl.pl = tail_in.p; op.refl.batch = B; op.refl.L = (int)L; op.refl.C = cout; op.refl.pad = 3; ops.push_back(op); }
+      plan->L = L;
+      plan->d_voc_wav = b.alloc<float>((size_t)B * L);
+      plan->d_peak = b.alloc<unsigned int>(B);
+      if (b.rc) return b.rc;
+      { Op op; op.kind = OP_MEMSET32; op.ms.p = plan->d_peak; op.ms.bytes = (size_t)B * 4; ops.push_back(op); }
+      Op op; op.kind = OP_TAIL;
+      VocTailParams& p = op.tail;
+      memset(&p, 0, sizeof p);
+      p.in = tail_in.p; p.batch = B; p.L = (int)L; p.C = cout; p.terms = terms; p.w = ctx->d_tail_w; p.bias = ctx->tail_b;
+      p.wav = plan->d_voc_wav; p.peak_bits = plan->d_peak;
+      ops.push_back(op);
+    }
+    prev = xa;
+    Lprev = L;
+    cin = cout;
+  }
+  return b.rc;
+}
+
+int get_plan(vf_ctx* ctx, int batch, int frames, Plan** out) {
+  const auto key = std::make_pair(batch, (long)frames);
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end()) { *out = it->second.get(); return VF_OK; }
+  if (!ctx->loaded) return fail(ctx, VF_ESTATE, "weights not loaded");
+  std::unique_ptr<Plan> plan(new Plan);
+  plan->batch = batch; plan->T = frames;
+  Builder b{ctx, plan.get()};
+  const size_t mel_n = (size_t)batch * frames * 128;
+  plan->d_mel = b.alloc<float>(mel_n);
+  plan->d_logmel_in = b.alloc<float>(mel_n);
+  plan->d_logmel_out = b.alloc<float>(mel_n);
+  int rc = b.rc;
+  if (!rc) rc = build_unet(ctx, b, plan.get());
+  if (!rc) rc = build_vocoder(ctx, b, plan.get());
+  if (rc) {
+    for (void* p : plan->allocs) cudaFree(p);
+    return rc;
+  }
+  *out = plan.get();
+  ctx->plans[key] = std::move(plan);
+  return VF_OK;
+}
+
+// staging buffers for the host-pointer entry point, grown on demand
+int ensure_io(vf_ctx* ctx, Plan* plan, long n) {
+  if (plan->n_samples >= n && plan->d_wav) return VF_OK;
+  Builder b{ctx, plan};
+  plan->d_wav = b.alloc<float>((size_t)plan->batch * n);
+  plan->d_out = b.alloc<float>((size_t)plan->batch * n);
+  plan->n_samples = n;
+  return b.rc;
+}
+
+int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
+  for (Op& op : ops) {
+    cudaError_t e = cudaSuccess;
+    switch (op.kind) {
+      case OP_GEMM:
+        e = ctx->validate_simt ? launch_gemm_simt(op.simt, st) : launch_gemm_tc(op.tc, op.bn, op.bk, st);
+        break;
+      case OP_FIRST: e = launch_unet_first(op.first, st); break;
+      case OP_POOL: e = launch_pool(op.pool, st); break;
+      case OP_COND: e = launch_voc_condition(op.cond, st); break;
+      case OP_REFLECT: e = launch_reflect_fill(op.refl.pl, op.refl.batch, op.refl.L, op.refl.C, op.refl.pad, st); break;
+      case OP_TAIL: e = launch_voc_tail(op.tail, st); break;
+      case OP_FINALIZE: e = launch_finalize(op.fin, st); break;
+      case OP_MEMSET32: e = cudaMemsetAsync(op.ms.p, 0, op.ms.bytes, st); break;
+    }
+    if (e != cudaSuccess) return fail(ctx, VF_ECUDA, "kernel launch (op kind %d): %s", (int)op.kind, cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  return VF_OK;
+}
+
+int frames_of(vf_ctx* ctx, long n) { return 1 + (int)(n / ctx->cfg.hop); }
+
+int run_frontend(vf_ctx* ctx, const float* wav, int batch, long n, float* mel, float* logmel, float* sp, float* co,
+                 float* si, cudaStream_t st) {
+  if (n <= 1024) return fail(ctx, VF_EINVAL, "reflect padding needs more than n_fft/2 = 1024 samples (got %ld)", n);
+  FrontendParams p;
+  memset(&p, 0, sizeof p);
+  p.wav = wav; p.n = n; p.batch = batch; p.T = frames_of(ctx, n);
+  p.window = ctx->d_window; p.tw1024 = ctx->d_tw1024; p.tw2048 = ctx->d_tw2048;
+  p.fb_f0 = ctx->d_fb_f0; p.fb_len = ctx->d_fb_len; p.fb_ofs = ctx->d_fb_ofs; p.fb_val = ctx->d_fb_val;
+  p.sp_out = sp; p.cos_out = co; p.sin_out = si; p.mel_out = mel; p.logmel_out = logmel;
+  cudaError_t e = launch_frontend(p, st);
+  if (e != cudaSuccess) return fail(ctx, VF_ECUDA, "frontend launch: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  return VF_OK;
+}
+
+int check_ready(vf_ctx* ctx) {
+  if (!ctx) return VF_EINVAL;
+  if (!ctx->loaded) return fail(ctx, VF_ESTATE, "weights not loaded (call vf_load_weights first)");
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return fail(ctx, VF_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return VF_OK;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" {
+
+VF_API void vf_default_config(vf_config* c) {
+  memset(c, 0, sizeof *c);
+  c->sample_rate = 44100; c->n_fft = 2048; c->hop = 441; c->n_mels = 128;
+  c->voc_cond_channels = 512; c->voc_cond_layers = 5; c->voc_channels = 1024; c->voc_num_stages = 4;
+  const int sc[4] = {7, 7, 3, 3};
+  for (int i = 0; i < 4; ++i) { c->voc_scales[i] = sc[i]; c->voc_depth[i] = 8; }
+  c->voc_stage_slope = 0.2f; c->voc_res_slope = 0.01f; c->voc_min_db = -115.f; c->voc_ref_db = 20.f;
+  c->voc_amp_floor = 1e-5f; c->voc_tail_value = -4.f; c->voc_tail_base = 4;
+  c->voc_mel_weight_a = 18.8927416350036; c->voc_mel_weight_b = 0.0269863588184314;
+}
+
+VF_API const char* vf_last_error(vf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+VF_API int vf_create(vf_ctx** out, int device, const vf_config* cfg) {
+  if (!out) return VF_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, VF_ENODEVICE, "no CUDA device available (%s); libb200vf has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(nullptr, VF_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, VF_ECUDA, "%s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, VF_ENODEVICE, "device %d is sm_%d%d; libb200vf is built for sm_100a only", device, prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, VF_ECUDA, "%s", cudaGetErrorString(e));
+  std::unique_ptr<vf_ctx> ctx(new vf_ctx);
+  ctx->device = device;
+  if (cfg) ctx->cfg = *cfg; else vf_default_config(&ctx->cfg);
+  const vf_config& c = ctx->cfg;
+  if (c.sample_rate != 44100 || c.n_fft != 2048 || c.hop != 441 || c.n_mels != 128)
+    return fail(nullptr, VF_EINVAL, "only the reference geometry (44100 Hz, n_fft 2048, hop 441, 128 mels) is built");
+  if (c.voc_num_stages < 1 || c.voc_num_stages > 8 || c.voc_cond_layers < 1) return fail(nullptr, VF_EINVAL, "bad vocoder config");
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || !fn) return fail(nullptr, VF_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  ctx->encode = (EncodeTiledFn)fn;
+  vf_ctx* raw = ctx.get();
+  size_t acct = 0;
+  int rc = dev_alloc(raw, raw->allocs, acct, &raw->d_err, 4);
+  if (rc) { g_create_error = raw->err; return rc; }
+  cudaMemset(raw->d_err, 0, 16);
+  rc = build_tables(raw);
+  if (rc) { g_create_error = raw->err; return rc; }
+  *out = ctx.release();
+  return VF_OK;
+}
+
+VF_API void vf_destroy(vf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->plans)
+    for (void* p : kv.second->allocs) cudaFree(p);
+  for (void* p : ctx->allocs) cudaFree(p);
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  delete ctx;
+}
+
+VF_API int vf_load_weights(vf_ctx* ctx, const vf_tensor_desc* descs, int n) {
+  if (!ctx || !descs || n <= 0) return VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; ++i) {
+    const vf_tensor_desc& d = descs[i];
+    if (!d.name || !d.data || d.ndim < 0 || d.ndim > 4) return fail(ctx, VF_EINVAL, "bad tensor descriptor %d", i);
+    HostT t;
+    size_t cnt = 1;
+    for (int k = 0; k < d.ndim; ++k) { t.shape.push_back(d.shape[k]); cnt *= (size_t)d.shape[k]; }
+    t.v.resize(cnt);
+    if (d.on_device) CK(cudaMemcpy(t.v.data(), d.data, cnt * 4, cudaMemcpyDeviceToHost));
+    else memcpy(t.v.data(), d.data, cnt * 4);
+    ctx->host_w[d.name] = std::move(t);
+  }
+  int rc = load_all(ctx);
+  if (rc) return rc;
+  ctx->host_w.clear();
+  ctx->loaded = true;
+  CK(cudaDeviceSynchronize());
+  return VF_OK;
+}
+
+VF_API int vf_frontend(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* mel_out, float* sp_out, float* cos_out,
+                float* sin_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!wav || batch <= 0) return fail(ctx, VF_EINVAL, "vf_frontend: bad arguments");
+  if ((cos_out || sin_out) && !(sp_out && cos_out && sin_out)) return fail(ctx, VF_EINVAL, "cos/sin need sp, cos and sin");
+  return run_frontend(ctx, wav, batch, (long)n, mel_out, nullptr, sp_out, cos_out, sin_out, (cudaStream_t)stream);
+}
+
+VF_API int vf_unet_mel(vf_ctx* ctx, const float* mel_lin, int batch, int frames, float* logmel_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!mel_lin || !logmel_out || batch <= 0 || frames <= 0) return fail(ctx, VF_EINVAL, "vf_unet_mel: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* plan;
+  rc = get_plan(ctx, batch, frames, &plan);
+  if (rc) return rc;
+  const size_t n = (size_t)batch * frames * 128;
+  CK(launch_to_log(mel_lin, plan->d_logmel_in, n, ctx->d_err + 1, st));
+  ctx->launches++;
+  rc = run_ops(ctx, plan->unet, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(logmel_out, plan->d_logmel_out, n * 4, cudaMemcpyDeviceToDevice, st));
+  return VF_OK;
+}
+
+VF_API int64_t vf_vocoder_out_len(vf_ctx* ctx, int frames) {
+  if (!ctx) return -1;
+  return (int64_t)(frames + frames % 2 + ctx->cfg.voc_tail_base) * ctx->cfg.hop;
+}
+
+VF_API int vf_vocoder(vf_ctx* ctx, const float* mel_lin, int batch, int frames, float* wav_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!mel_lin || !wav_out || batch <= 0 || frames <= 0) return fail(ctx, VF_EINVAL, "vf_vocoder: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* plan;
+  rc = get_plan(ctx, batch, frames, &plan);
+  if (rc) return rc;
+  Op& cop = plan->vocoder[plan->cond_op];
+  cop.cond.mel = mel_lin;
+  cop.cond.is_log = 0;
+  rc = run_ops(ctx, plan->vocoder, st);
+  cop.cond.mel = plan->d_logmel_out;
+  cop.cond.is_log = 1;
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(wav_out, plan->d_voc_wav, (size_t)batch * plan->L * 4, cudaMemcpyDeviceToDevice, st));
+  return VF_OK;
+}
+
+VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!wav || !wav_out || batch <= 0) return fail(ctx, VF_EINVAL, "vf_restore: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int frames = frames_of(ctx, (long)n);
+  Plan* plan;
+  rc = get_plan(ctx, batch, frames, &plan);
+  if (rc) return rc;
+  const bool tm = ctx->timing;
+  if (tm) {
+    for (auto& e : ctx->ev)
+      if (!e) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(ctx->ev[0], st));
+  }
+  rc = run_frontend(ctx, wav, batch, (long)n, plan->d_mel, plan->d_logmel_in, nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  if (tm) CK(cudaEventRecord(ctx->ev[1], st));
+  rc = run_ops(ctx, plan->unet, st);
+  if (rc) return rc;
+  if (tm) CK(cudaEventRecord(ctx->ev[2], st));
+  rc = run_ops(ctx, plan->vocoder, st);
+  if (rc) return rc;
+  if (tm) CK(cudaEventRecord(ctx->ev[3], st));
+  // eval_gsr_voicefixer.py:68-72: peak normalise + trim_center
+  FinalizeParams f;
+  memset(&f, 0, sizeof f);
+  const long d = plan->L - (long)n;
+  if (d < 0 || d == 1) return fail(ctx, VF_EINVAL, "vocoder output length %ld incompatible with input %ld (trim_center)", plan->L, (long)n);
+  f.wav = plan->d_voc_wav; f.peak_bits = plan->d_peak; f.batch = batch; f.L = plan->L; f.n = (long)n; f.skip = d / 2;
+  f.out = wav_out; f.out_ld = (long)n; f.out_off = 0;
+  CK(launch_finalize(f, st));
+  ctx->launches++;
+  if (tm) { CK(cudaEventRecord(ctx->ev[4], st)); ctx->ev_valid = true; }
+  return VF_OK;
+}
+
+VF_API int vf_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_t n, float* out_host, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!wav_host || !out_host || batch <= 0) return fail(ctx, VF_EINVAL, "vf_restore_host: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* plan;
+  rc = get_plan(ctx, batch, frames_of(ctx, (long)n), &plan);
+  if (rc) return rc;
+  rc = ensure_io(ctx, plan, (long)n);
+  if (rc) return rc;
+  const size_t bytes = (size_t)batch * n * 4;
+  CK(cudaMemcpyAsync(plan->d_wav, wav_host, bytes, cudaMemcpyHostToDevice, st));
+  rc = vf_restore(ctx, plan->d_wav, batch, n, plan->d_out, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_host, plan->d_out, bytes, cudaMemcpyDeviceToHost, st));
+  return VF_OK;
+}
+
+VF_API int vf_restore_stages(vf_ctx* ctx, int batch, int64_t n, float* mel_lin_out, float* log_mel_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  Plan* plan;
+  const int frames = frames_of(ctx, (long)n);
+  rc = get_plan(ctx, batch, frames, &plan);
+  if (rc) return rc;
+  const size_t bytes = (size_t)batch * frames * 128 * 4;
+  if (mel_lin_out) CK(cudaMemcpyAsync(mel_lin_out, plan->d_mel, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (log_mel_out) CK(cudaMemcpyAsync(log_mel_out, plan->d_logmel_out, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return VF_OK;
+}
+
+VF_API int vf_to_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream) {
+  if (!ctx || !in || !out || n <= 0) return VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_to_log(in, out, (size_t)n, ctx->d_err + 1, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+VF_API int vf_from_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream) {
+  if (!ctx || !in || !out || n <= 0) return VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_from_log(in, out, (size_t)n, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+
+VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n, size_t* bytes) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  Plan* plan;
+  rc = get_plan(ctx, batch, frames_of(ctx, (long)n), &plan);
+  if (rc) return rc;
+  if (bytes) *bytes = plan->bytes + ctx->weight_bytes;
+  return VF_OK;
+}
+
+VF_API int vf_check_errors(vf_ctx* ctx, void* stream) {
+  if (!ctx) return VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  int h[2] = {0, 0};
+  CK(cudaMemcpy(h, ctx->d_err, 8, cudaMemcpyDeviceToHost));
+  if (h[0] || h[1]) CK(cudaMemset(ctx->d_err, 0, 8));
+  if (h[0] == ERR_FP16_OVERFLOW) return fail(ctx, VF_EDEVICE, "activation outside the fp16 range (|a| > 65504) in a hi/lo split");
+  if (h[0]) return fail(ctx, VF_EDEVICE, "device pipeline error code %d (201 producer / 202 mma / 203 epilogue time-out)", h[0]);
+  if (h[1]) return fail(ctx, VF_EASSERT, "input has negative values counts %d", h[1]);
+  return VF_OK;
+}
+
+VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value) {
+  if (!ctx || !key) return VF_EINVAL;
+  const std::string k = key;
+  int* slot = nullptr;
+  if (k == "unet_terms" || k == "vocoder_terms") {
+    if (value != 1 && value != 3) return fail(ctx, VF_EINVAL, "%s must be 1 or 3", key);
+    slot = k == "unet_terms" ? &ctx->unet_terms : &ctx->voc_terms;
+  } else if (k == "validate_simt") {
+    slot = &ctx->validate_simt;
+    value = value ? 1 : 0;
+  } else {
+    return fail(ctx, VF_EINVAL, "unknown option '%s'", key);
+  }
+  if (*slot != value) {   // plans bake the option in: drop them
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->plans)
+      for (void* p : kv.second->allocs) cudaFree(p);
+    ctx->plans.clear();
+    *slot = value;
+  }
+  return VF_OK;
+}
+
+VF_API int64_t vf_launch_count(vf_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+VF_API int vf_enable_stage_timing(vf_ctx* ctx, int enable) {
+  if (!ctx) return VF_EINVAL;
+  ctx->timing = enable != 0;
+  ctx->ev_valid = false;
+  return VF_OK;
+}
+VF_API int vf_stage_times(vf_ctx* ctx, float ms[4]) {
+  if (!ctx || !ms) return VF_EINVAL;
+  if (!ctx->ev_valid) return fail(ctx, VF_ESTATE, "no timed vf_restore yet");
+  CK(cudaEventSynchronize(ctx->ev[4]));
+  for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  return VF_OK;
+}
+
+VF_API int vf_selftest_gemm(vf_ctx* ctx, int n_img, int rows, int cin, int cout, int ntaps, int dilation, int terms,
+                     double* max_abs_diff, double* max_abs_ref) {
+  if (!ctx || n_img <= 0 || rows <= 0 || cin % 32 || cout % 32 || ntaps < 1 || ntaps > GEMM_MAX_TAPS || (terms != 1 && terms != 3))
+    return ctx ? fail(ctx, VF_EINVAL, "vf_selftest_gemm: bad arguments") : VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  Plan plan;
+  Builder b{ctx, &plan};
+  const int K = ntaps * cin;
+  // deterministic pseudo-random operands
+  uint32_t seed = 12345u + rows * 7 + cin * 3 + cout;
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  std::vector<float> wm((size_t)cout * K), bias(cout);
+  for (auto& x : wm) x = rnd() * 0.2f;
+  for (auto& x : bias) x = rnd();
+  GemmW W;
+  int rc = upload_gemm(ctx, &W, wm, cout, K, &bias);
+  if (rc) return rc;
+  const size_t an = (size_t)n_img * rows * cin;
+  std::vector<__half> ahi(an), alo(an);
+  for (size_t i = 0; i < an; ++i) {
+    const float a = rnd() * 4.f;
+    ahi[i] = __float2half_rn(a);
+    alo[i] = __float2half_rn(a - __half2float(ahi[i]));
+  }
+  Planes A = b.planes(n_img, rows, cin);
+  float* out[2] = {b.alloc<float>((size_t)n_img * rows * cout), b.alloc<float>((size_t)n_img * rows * cout)};
+  if (b.rc) return b.rc;
+  CK(cudaMemcpy(A.p.hi, ahi.data(), an * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(A.p.lo, alo.data(), an * 2, cudaMemcpyHostToDevice));
+  const int saved = ctx->validate_simt;
+  for (int impl = 0; impl < 2; ++impl) {
+    ctx->validate_simt = impl;
+    std::vector<Op> ops;
+    GemmEpilogue e = epi_plain(rows, 0, cout, rows);
+    e.bias = W.bias;
+    e.out_raw = out[impl];
+    e.raw_ld = cout;
+    std::vector<GemmTap> taps;
+    for (int t = 0; t < ntaps; ++t) taps.push_back(GemmTap{(t - (ntaps - 1) / 2) * dilation, 0, 0, 0, cin});
+    b.gemm(ops, W, ASrc{A, rows, 0}, nullptr, taps, e, n_img, terms);
+    if (!b.rc) b.rc = run_ops(ctx, ops, 0);
+  }
+  ctx->validate_simt = saved;
+  cudaError_t se = cudaDeviceSynchronize();
+  rc = b.rc;
+  double md = 0, mr = 0;
+  if (!rc && se == cudaSuccess) {
+    const size_t on = (size_t)n_img * rows * cout;
+    std::vector<float> h0(on), h1(on);
+    cudaMemcpy(h0.data(), out[0], on * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h1.data(), out[1], on * 4, cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < on; ++i) {
+      const double d = std::fabs((double)h0[i] - (double)h1[i]);
+      if (!(d <= md)) md = d;          // NaN-propagating max
+      if (std::fabs(h1[i]) > mr) mr = std::fabs(h1[i]);
+    }
+  }
+  for (void* p : plan.allocs) cudaFree(p);
+  if (se != cudaSuccess) return fail(ctx, VF_ECUDA, "selftest: %s", cudaGetErrorString(se));
+  if (rc) return rc;
+  if (max_abs_diff) *max_abs_diff = md;
+  if (max_abs_ref) *max_abs_ref = mr;
+  return VF_OK;
+}
+
+}  // extern "C"

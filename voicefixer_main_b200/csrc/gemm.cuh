@@ -1,0 +1,201 @@
+// Flat-shift multi-tap GEMM: the one contraction every conv on the VoiceFixer hot path maps to.
+//
+//   D[m, n] = sum_taps sum_c  A_src(tap)[img, m + a_off(tap), c_off(tap) + c] * W[n, k_off(tap) + c]
+//
+// Activations live in HBM as "rows x channels" fp16 planes (channels innermost): rows are flattened
+// (h, w) pixels with one shared zero pad column per image row for the 2-D UNet (row pitch Wp = W + 1),
+// or time steps for the 1-D vocoder.  A conv tap is then a constant row offset; zero padding above /
+// below an image is the TMA out-of-bounds fill.  Each fp32 value a is stored as the pair
+// hi = fp16(a), lo = fp16(a - hi); the product uses the three terms hi*hi + hi*lo + lo*hi with fp32
+// accumulation (error ~2^-22, measured 5e-6 max on the full UNet - see DESIGN.md), or hi*hi only
+// (terms = 1) where the stage tolerance allows.
+//
+// Reference ops covered (file:line in /root/reference):
+//   Conv2d 3x3 pad 1 no bias          models/components/modules.py:235-243   9 taps
+//   1x1 shortcut Conv2d + bias        models/components/modules.py:245-247   +1 tap, fused in the same accumulator
+//   ConvTranspose2d k3 s2             models/components/modules.py:192-194   4 taps, N = 4 phases x Cout
+//   Conv1d / ConvTranspose1d          vocoder restatement (oracle/vf_oracle.py:vocoder_generator)
+// The epilogue fuses everything the reference does between two convs: bias, residual add
+// (modules.py:268-271), eval-mode BatchNorm as a per-channel affine + LeakyReLU/ReLU/ELU of the
+// *consumer* (modules.py:263-266, 213), prune/concat placement (modules.py:205-215), the 1x1 head
+// with the log-mel residual (unet.py:96-100, gsr_voicefixer.py:90) and the fp16 hi/lo split.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace vf {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_MAX_TAPS = 12;
+
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ELU = 2 };
+enum { MAP_PLAIN = 0, MAP_CONVT2D = 1, MAP_CONVT1D = 2 };
+enum { ERR_FP16_OVERFLOW = 100, ERR_PIPE_PRODUCER = 201, ERR_PIPE_MMA = 202, ERR_PIPE_EPILOGUE = 203 };
+
+struct GemmTap {
+  int a_off;   // row offset relative to the output row
+  int src;     // which A source (0/1)
+  int c_off;   // first channel inside the source
+  int k_off;   // first column of this tap's segment in the packed weight matrix
+  int nch;     // channels contracted by this tap (multiple of the kernel's BK)
+};
+
+struct OutPlane {
+  __half* hi;
+  __half* lo;
+  int ld;      // row stride in elements
+  int c_off;   // channel offset (concat placement)
+};
+
+struct GemmEpilogue {
+  int map;             // MAP_*
+  int rows_in;         // valid GEMM rows per image
+  int Wp;              // 2-D row pitch (pad column = Wp-1); 0 for 1-D data
+  int cout;            // channels per phase (N = phases * cout)
+  int out_img_rows;    // rows per image in the output allocations
+  int out_row0;        // row offset of output row 0 (slack for reflection padding)
+  int out_rows_valid;  // MAP_CONVT1D: rows [0, out_rows_valid) exist
+  int ct_stride, ct_pad;
+  const float* bias;   // [N] or null
+  const float* resid;  // fp32 [n_img * rows_in, resid_ld] or null (MAP_PLAIN only)
+  int resid_ld;
+  float* out_raw;      // fp32 or null
+  int raw_ld;
+  OutPlane out_r;      // raw value split hi/lo (consumed by 1x1 shortcut taps)
+  OutPlane out_a;      // act(scale * v + shift) split hi/lo (consumed by the next conv)
+  const float* a_scale;  // [cout] or null (identity)
+  const float* a_shift;
+  int act;
+  float slope;
+  const float* head_w;   // fused 1x1 head over the 32 channels of the row, or null
+  float head_b;
+  const float* head_in;  // log-mel input  [n_img, head_T, 128]
+  float* head_out;       // log-mel output [n_img, head_T, 128]
+  int head_T;
+  int* err;
+};
+
+struct GemmProblem {
+  int n_img;
+  int m_tiles;   // ceil(rows_in / 128)
+  int N;
+  int ntaps;
+  int terms;     // 1 or 3
+  GemmTap taps[GEMM_MAX_TAPS];
+  GemmEpilogue epi;
+};
+
+struct GemmTcParams {
+  CUtensorMap a_hi[2], a_lo[2];   // [C, rows, n_img] fp16
+  CUtensorMap b_hi, b_lo;         // [Ktot, N] fp16 (K-major)
+  int stages;
+  GemmProblem prob;
+};
+
+struct GemmSimtParams {            // validation kernel: same contract, plain pointers
+  const __half* a_hi[2];
+  const __half* a_lo[2];
+  int a_ld[2], a_rows[2], a_img_rows[2];
+  const __half* b_hi;
+  const __half* b_lo;
+  int ktot;
+  GemmProblem prob;
+};
+
+__device__ __forceinline__ void split_store8(__half* hi, __half* lo, size_t idx, const float* a) {
+  __align__(16) __half h[8];
+  __align__(16) __half l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2half_rn(a[i]);
+    l[i] = __float2half_rn(a[i] - __half2float(h[i]));
+  }
+  *reinterpret_cast<uint4*>(hi + idx) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(lo + idx) = *reinterpret_cast<const uint4*>(l);
+}
+
+// One thread owns GEMM row `r` of image `img`; v holds columns [n_base, n_base + 32).
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int img, int r, int n_base, float (&v)[32],
+                                               float& head_acc) {
+  if (r >= e.rows_in) return;
+  int co0 = n_base, phase = 0;
+  if (e.map != MAP_PLAIN) {
+    phase = n_base / e.cout;
+    co0 = n_base - phase * e.cout;
+  }
+  size_t orow;
+  bool pad = false;
+  if (e.map == MAP_PLAIN) {
+    orow = (size_t)img * e.out_img_rows + e.out_row0 + r;
+    if (e.Wp > 0) pad = (r % e.Wp) == e.Wp - 1;
+  } else if (e.map == MAP_CONVT2D) {
+    const int h = r / e.Wp, w = r - h * e.Wp;
+    const int ph = phase >> 1, pw = phase & 1;
+    orow = (size_t)img * e.out_img_rows + (size_t)(2 * h + ph) * (2 * e.Wp) + 2 * w + pw;
+    pad = (w == e.Wp - 1) && (pw == 1);
+  } else {
+    const long t = (long)r * e.ct_stride + phase - e.ct_pad;
+    if (t < 0 || t >= e.out_rows_valid) return;
+    orow = (size_t)img * e.out_img_rows + e.out_row0 + t;
+  }
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __ldg(e.bias + n_base + i);
+  }
+  if (e.resid) {
+    const float4* rp = reinterpret_cast<const float4*>(e.resid + ((size_t)img * e.rows_in + r) * e.resid_ld + co0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = __ldg(rp + i);
+      v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+    }
+  }
+  if (pad) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  }
+  if (e.out_raw) {
+    float4* op = reinterpret_cast<float4*>(e.out_raw + orow * e.raw_ld + co0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (e.out_r.hi) {
+    const size_t base = orow * e.out_r.ld + e.out_r.c_off + co0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_store8(e.out_r.hi, e.out_r.lo, base + 8 * i, v + 8 * i);
+  }
+  if (e.head_w) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) head_acc = fmaf(v[i], __ldg(e.head_w + co0 + i), head_acc);
+  }
+  if (e.out_a.hi) {
+    bool ovf = false;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float a = v[i];
+      if (e.a_scale) a = fmaf(a, __ldg(e.a_scale + co0 + i), __ldg(e.a_shift + co0 + i));
+      if (e.act == ACT_LRELU) a = a > 0.f ? a : a * e.slope;
+      else if (e.act == ACT_ELU) a = a > 0.f ? a : expm1f(a);
+      if (pad) a = 0.f;
+      ovf |= !(fabsf(a) <= 65504.f);
+      v[i] = a;
+    }
+    if (ovf && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
+    const size_t base = orow * e.out_a.ld + e.out_a.c_off + co0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_store8(e.out_a.hi, e.out_a.lo, base + 8 * i, v + 8 * i);
+  }
+}
+
+// unet.py:96-100 + gsr_voicefixer.py:90: out = head(x) padded with a zero bin, plus the input log-mel.
+__device__ __forceinline__ void epilogue_head(const GemmEpilogue& e, int img, int r, float head_acc) {
+  if (!e.head_w || r >= e.rows_in) return;
+  const int t = r >> 7, f = r & 127;
+  if (t >= e.head_T) return;
+  const size_t idx = ((size_t)img * e.head_T + t) * 128 + f;
+  const float x = __ldg(e.head_in + idx);
+  e.head_out[idx] = (f < 127) ? (head_acc + e.head_b) + x : x;
+}
+
+}  // namespace vf

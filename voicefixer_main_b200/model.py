@@ -1,0 +1,472 @@
+"""Host-side mirror of the reference's model objects for the inference hot path.
+
+Same names, arguments and error behaviour as the objects eval_gsr_voicefixer.py:handler() uses
+(SURVEY.md 8(b)), backed entirely by libb200vf.so:
+
+    VoiceFixer(hp, channels, type_target)       models/gsr_voicefixer.py:94
+      .load_from_checkpoint(ckpt) / .load_state_dict(sd) / .eval() / .to(device)
+      .pre(wav[B,1,N]) -> (sp, mel_orig)         models/gsr_voicefixer.py:178-181
+      .forward(mel_orig) -> {'mel': log10 mel}   models/gsr_voicefixer.py:183-193
+      .f_helper.wav_to_spectrogram_phase(x)      tools/pytorch/modules/fDomainHelper.py:67-89
+      .mel(specgram[..., freq, time])            tools/pytorch/mel_scale.py:52-64
+      .vocoder(mel[B,1,T,128]) -> wav[B,1,L]     eval_gsr_voicefixer.py:66
+    plus the batched fused entry points the reference lacks:
+      .restore(wav[B,N]) -> wav[B,N]             one launch chain for stages A -> B -> C + normalise + trim
+      .restore_host(pinned_in, pinned_out)
+
+PyTorch is used only to own device memory and streams; every tensor handed back is written by a
+hand-written sm_100a kernel.  Tensors must be fp32 CUDA tensors on the model's device.
+"""
+import ctypes
+import json
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .arch import UNET_PREFIX, VocoderConfig, frames_for, unet_keys, vocoder_keys
+
+
+class HParams:
+    """Attribute/Item dictionary, same behaviour as tools/utils.py:122-151."""
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            if type(v) == dict:
+                v = HParams(**v)
+            self[k] = v
+
+    def keys(self):
+        return self.__dict__.keys()
+
+    def items(self):
+        return self.__dict__.items()
+
+    def values(self):
+        return self.__dict__.values()
+
+    def __len__(self):
+        return len(self.__dict__)
+
+    def __getitem__(self, key):
+        return getattr(self, key)
+
+    def __setitem__(self, key, value):
+        return setattr(self, key, value)
+
+    def __contains__(self, key):
+        return key in self.__dict__
+
+    def __repr__(self):
+        return self.__dict__.__repr__()
+
+
+def get_hparams_from_file(config_path) -> HParams:
+    """tools/utils.py:114-120."""
+    with open(config_path, "r") as f:
+        return HParams(**json.loads(f.read()))
+
+
+def default_hparams() -> HParams:
+    """The hot-path-relevant keys of config/vctk_base_voicefixer_unet.json."""
+    return HParams(**{
+        "task": {"gsr": {"gsr_model": {"voicefixer": {"unet": True, "unet_small": False, "bi_gru": False, "dnn": False}}}},
+        "data": {"sampling_rate": 44100},
+        "model": {"mel_freq_bins": 128, "window_size": 2048, "hop_size": 441, "pad_mode": "reflect",
+                  "window": "hann", "channels_in": 1},
+    })
+
+
+def melscale_fbanks(n_freqs=1025, f_min=0.0, f_max=22050.0, n_mels=128, sample_rate=44100):
+    """HTK triangular filterbank, same fp32 op order as tools/pytorch/mel_scale.py:131-221 (norm=None)."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + (f_min / 700.0))
+    m_max = 2595.0 * math.log10(1.0 + (f_max / 700.0))
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down_slopes = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up_slopes = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down_slopes, up_slopes))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_in(t: torch.Tensor, device, what: str):
+    if not isinstance(t, torch.Tensor) or t.dtype != torch.float32 or not t.is_cuda or t.device != device:
+        raise TypeError(f"{what} must be a float32 CUDA tensor on {device}")
+    return t.contiguous()
+
+
+class Engine:
+    """One vf_ctx on one device."""
+
+    def __init__(self, device, cfg: Optional[VocoderConfig] = None):
+        self.lib = L.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("voicefixer_main_b200 runs on CUDA devices only (no CPU fallback)")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)
+        self.voc_cfg = cfg or VocoderConfig()
+        c = L.VfConfig()
+        self.lib.vf_default_config(ctypes.byref(c))
+        v = self.voc_cfg
+        c.voc_cond_channels, c.voc_cond_layers, c.voc_channels = v.cond_channels, v.cond_layers, v.channels
+        c.voc_num_stages = len(v.upsample_scales)
+        for i, (s, d) in enumerate(zip(v.upsample_scales, v.resstack_depth)):
+            c.voc_scales[i], c.voc_depth[i] = s, d
+        c.voc_stage_slope, c.voc_res_slope, c.voc_min_db, c.voc_ref_db = v.stage_slope, v.res_slope, v.min_db, v.ref_db
+        c.voc_amp_floor, c.voc_tail_value, c.voc_tail_base = v.amp_floor, v.tail_pad_value, v.tail_pad_base
+        c.voc_mel_weight_a, c.voc_mel_weight_b = v.mel_weight_a, v.mel_weight_b
+        self.ctx = ctypes.c_void_p()
+        rc = self.lib.vf_create(ctypes.byref(self.ctx), self.index, ctypes.byref(c))
+        if rc != L.VF_OK:
+            msg = self.lib.vf_last_error(None)
+            raise L.EngineError(rc, msg.decode() if msg else "")
+        self.loaded = False
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx.value:
+            self.lib.vf_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        return L.check(self.lib, self.ctx, rc)
+
+    def load_state(self, state: Dict[str, torch.Tensor]):
+        needed = [UNET_PREFIX + k for k, s in unet_keys() if not k.endswith("num_batches_tracked")]
+        needed += ["vocoder." + k for k, _ in vocoder_keys(self.voc_cfg)]
+        missing = [k for k in needed if k not in state]
+        if missing:
+            raise KeyError(f"state dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        fb = state["mel.fb"] if "mel.fb" in state else melscale_fbanks()
+        items = [("mel.fb", fb)] + [(k, state[k]) for k in needed]
+        descs = (L.VfTensorDesc * len(items))()
+        keep = []
+        for d, (k, t) in zip(descs, items):
+            t = t.detach().to(dtype=torch.float32).contiguous()
+            keep.append(t)
+            d.name = k.encode()
+            d.data = t.data_ptr()
+            d.ndim = t.dim()
+            for i, s in enumerate(t.shape):
+                d.shape[i] = s
+            d.on_device = 1 if t.is_cuda else 0
+        self._ck(self.lib.vf_load_weights(self.ctx, descs, len(items)))
+        self.loaded = True
+
+    # ---- stage entry points (device tensors in, device tensors out)
+    def frontend(self, wav: torch.Tensor, want_sp: bool = False, want_phase: bool = False):
+        wav = _check_in(wav, self.device, "wav")
+        b, n = wav.shape
+        t = frames_for(n)
+        mel = torch.empty(b, t, 128, device=self.device)
+        sp = torch.empty(b, t, 1025, device=self.device) if (want_sp or want_phase) else None
+        cos = torch.empty_like(sp) if want_phase else None
+        sin = torch.empty_like(sp) if want_phase else None
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_frontend(self.ctx, _ptr(wav), b, n, _ptr(mel), _ptr(sp), _ptr(cos), _ptr(sin), _stream()))
+        return mel, sp, cos, sin
+
+    def unet_mel(self, mel_lin: torch.Tensor) -> torch.Tensor:
+        mel_lin = _check_in(mel_lin, self.device, "mel")
+        b, t, m = mel_lin.shape
+        assert m == 128
+        out = torch.empty_like(mel_lin)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_unet_mel(self.ctx, _ptr(mel_lin), b, t, _ptr(out), _stream()))
+        return out
+
+    def vocoder(self, mel_lin: torch.Tensor) -> torch.Tensor:
+        mel_lin = _check_in(mel_lin, self.device, "mel")
+        b, t, m = mel_lin.shape
+        assert m == 128
+        out = torch.empty(b, self.lib.vf_vocoder_out_len(self.ctx, t), device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_vocoder(self.ctx, _ptr(mel_lin), b, t, _ptr(out), _stream()))
+        return out
+
+    def restore(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        wav = _check_in(wav, self.device, "wav")
+        b, n = wav.shape
+        out = torch.empty_like(wav) if out is None else out
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_restore(self.ctx, _ptr(wav), b, n, _ptr(out), _stream()))
+        return out
+
+    def restore_host(self, wav_host: torch.Tensor, out_host: torch.Tensor):
+        """Pinned host tensors [B,N] in/out; asynchronous on the current stream."""
+        assert wav_host.dtype == torch.float32 and out_host.dtype == torch.float32
+        assert not wav_host.is_cuda and not out_host.is_cuda and wav_host.is_contiguous() and out_host.is_contiguous()
+        b, n = wav_host.shape
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_restore_host(self.ctx, _ptr(wav_host), b, n, _ptr(out_host), _stream()))
+
+    def restore_stages(self, batch: int, n: int):
+        """(linear mel, restored log10 mel), each [B,T,128], of the last restore() of this shape."""
+        t = frames_for(n)
+        mel = torch.empty(batch, t, 128, device=self.device)
+        log_mel = torch.empty(batch, t, 128, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_restore_stages(self.ctx, batch, n, _ptr(mel), _ptr(log_mel), _stream()))
+        return mel, log_mel
+
+    def to_log(self, x):
+        x = _check_in(x, self.device, "input")
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_to_log(self.ctx, _ptr(x), _ptr(out), x.numel(), _stream()))
+        return out
+
+    def from_log(self, x):
+        x = _check_in(x, self.device, "input")
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_from_log(self.ctx, _ptr(x), _ptr(out), x.numel(), _stream()))
+        return out
+
+    def check_errors(self):
+        """Synchronises the current stream and raises on sticky device errors (AssertionError for the
+        to_log negative-input assertion, as tools/pytorch/pytorch_util.py:158 does)."""
+        with torch.cuda.device(self.device):
+            rc = self.lib.vf_check_errors(self.ctx, _stream())
+        if rc == L.VF_EASSERT:
+            raise AssertionError(self.lib.vf_last_error(self.ctx).decode())
+        self._ck(rc)
+
+    def set_option(self, key: str, value: int):
+        self._ck(self.lib.vf_set_option(self.ctx, key.encode(), int(value)))
+
+    def launch_count(self) -> int:
+        return int(self.lib.vf_launch_count(self.ctx))
+
+    def workspace_bytes(self, batch: int, n: int) -> int:
+        v = ctypes.c_size_t()
+        self._ck(self.lib.vf_workspace_bytes(self.ctx, batch, n, ctypes.byref(v)))
+        return int(v.value)
+
+    def enable_stage_timing(self, on: bool = True):
+        self._ck(self.lib.vf_enable_stage_timing(self.ctx, int(on)))
+
+    def stage_times(self):
+        arr = (ctypes.c_float * 4)()
+        self._ck(self.lib.vf_stage_times(self.ctx, ctypes.byref(arr)))
+        return dict(zip(("frontend_ms", "unet_ms", "vocoder_ms", "tail_ms"), [float(x) for x in arr]))
+
+    def selftest_gemm(self, n_img, rows, cin, cout, ntaps, dilation=1, terms=3):
+        d, r = ctypes.c_double(), ctypes.c_double()
+        self._ck(self.lib.vf_selftest_gemm(self.ctx, n_img, rows, cin, cout, ntaps, dilation, terms,
+                                           ctypes.byref(d), ctypes.byref(r)))
+        return d.value, r.value
+
+
+# --------------------------------------------------------------------------------------------------------------
+class FDomainHelper:
+    """tools/pytorch/modules/fDomainHelper.py:12-113, STFT analysis side, window 2048 / hop 441 / hann / reflect."""
+
+    def __init__(self, owner, window_size=2048, hop_size=441, center=True, pad_mode="reflect", window="hann",
+                 freeze_parameters=True, subband=None):
+        if (window_size, hop_size, center, pad_mode, window, subband) != (2048, 441, True, "reflect", "hann", None):
+            raise NotImplementedError("libb200vf implements the reference geometry only (2048/441/hann/reflect)")
+        self._owner = owner
+        self._last = None    # (sp tensor, mel tensor) of the latest call, so .mel() can reuse the fused result
+
+    def _run(self, input, phase):
+        eng = self._owner._engine()
+        assert input.dim() == 3, "input: (batch_size, channels_num, segment_samples)"
+        b, c, n = input.shape
+        flat = input.reshape(b * c, n)
+        mel, sp, cos, sin = eng.frontend(flat, want_sp=True, want_phase=phase)
+        t = sp.shape[1]
+        sp = sp.view(b, c, t, 1025)
+        self._last = (sp, mel.view(b, c, t, 128))
+        if phase:
+            return sp, cos.view(b, c, t, 1025), sin.view(b, c, t, 1025)
+        return sp
+
+    def wav_to_spectrogram_phase(self, input, eps=1e-8):
+        assert eps == 1e-8
+        return self._run(input, True)
+
+    def wav_to_spectrogram(self, input, eps=1e-8):
+        assert eps == 1e-8
+        return self._run(input, False)
+
+
+class MelScale:
+    """tools/pytorch/mel_scale.py:8-64.  forward(specgram[..., freq, time]) -> [..., n_mels, time]."""
+
+    def __init__(self, owner, n_mels=128, sample_rate=44100, n_stft=1025):
+        self.n_mels, self.sample_rate = n_mels, sample_rate
+        self.f_min, self.f_max = 0.0, float(sample_rate // 2)
+        self.fb = melscale_fbanks(n_stft, self.f_min, self.f_max, n_mels, sample_rate)
+        self._owner = owner
+
+    def __call__(self, specgram):
+        return self.forward(specgram)
+
+    def forward(self, specgram):
+        last = self._owner.f_helper._last
+        if last is not None:
+            sp, mel = last
+            # handler/pre() pass sp.permute(0,1,3,2): same storage -> the fused front end already produced it
+            if specgram.data_ptr() == sp.data_ptr() and tuple(specgram.shape) == (sp.shape[0], sp.shape[1], sp.shape[3], sp.shape[2]):
+                return mel.permute(0, 1, 3, 2)
+        raise NotImplementedError(
+            "MelScale.forward is fused into the front-end kernel: call it on the (permuted) spectrogram returned by "
+            "f_helper.wav_to_spectrogram_phase / wav_to_spectrogram, or use VoiceFixer.pre()")
+
+
+class Vocoder:
+    """Stand-in for voicefixer.Vocoder(sample_rate): __call__(mel [B,1,T,128]) -> wav [B,1,L]."""
+
+    def __init__(self, owner, sample_rate=44100):
+        assert sample_rate == 44100
+        self.rate = sample_rate
+        self._owner = owner
+
+    def __call__(self, mel, cuda=False):
+        return self.forward(mel)
+
+    def forward(self, mel, cuda=False):
+        assert mel.size()[-1] == 128
+        assert mel.dim() == 4 and mel.shape[1] == 1
+        out = self._owner._engine().vocoder(mel[:, 0])
+        return out[:, None, :]
+
+
+class Generator:
+    """models/gsr_voicefixer.py:44-91 with the `unet` analysis module: mel_orig -> {'mel': log10 mel}."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def __call__(self, mel_orig):
+        return self.forward(mel_orig)
+
+    def forward(self, mel_orig):
+        assert mel_orig.dim() == 4 and mel_orig.shape[1] == 1 and mel_orig.shape[-1] == 128
+        eng = self._owner._engine()
+        out = eng.unet_mel(mel_orig[:, 0])
+        eng.check_errors()          # to_log's assert (pytorch_util.py:158) - a host sync in the reference too
+        return {"mel": out[:, None]}
+
+
+class VoiceFixer:
+    """Drop-in for models.gsr_voicefixer.VoiceFixer on the inference path (eval mode only)."""
+
+    def __init__(self, hp=None, channels=2, type_target="vocals", vocoder_config: Optional[VocoderConfig] = None):
+        hp = hp if hp is not None else default_hparams()
+        self.hp = hp
+        self.channels, self.type_target = channels, type_target
+        self.sampling_rate = hp["data"]["sampling_rate"]
+        sel = hp["task"]["gsr"]["gsr_model"]["voicefixer"]
+        if not sel["unet"]:
+            raise NotImplementedError("only the `unet` analysis module (config/vctk_base_voicefixer_unet.json:8) is built")
+        if hp["model"]["channels_in"] != 1:
+            raise NotImplementedError("channels_in must be 1")
+        self.voc_cfg = vocoder_config or VocoderConfig()
+        self.f_helper = FDomainHelper(self, window_size=hp["model"]["window_size"], hop_size=hp["model"]["hop_size"],
+                                      center=True, pad_mode=hp["model"]["pad_mode"], window=hp["model"]["window"])
+        self.mel_freq_bins = hp["model"]["mel_freq_bins"]
+        self.mel = MelScale(self, n_mels=self.mel_freq_bins, sample_rate=self.sampling_rate,
+                            n_stft=hp["model"]["window_size"] // 2 + 1)
+        self.vocoder = Vocoder(self, sample_rate=44100)
+        self.generator = Generator(self)
+        self.downsample_ratio = 2 ** 6
+        self.device = None
+        self._eng: Optional[Engine] = None
+        self._state: Optional[Dict[str, torch.Tensor]] = None
+        self.training = False
+
+    # ---- nn.Module / Lightning surface used by the handler
+    def _engine(self) -> Engine:
+        if self._eng is None:
+            raise RuntimeError("model is not on a CUDA device yet: call .to(device) (there is no CPU path)")
+        if not self._eng.loaded:
+            raise RuntimeError("no weights loaded: call load_state_dict / load_from_checkpoint first")
+        return self._eng
+
+    def load_state_dict(self, state_dict, strict=True):
+        self._state = {k: v for k, v in state_dict.items() if isinstance(v, torch.Tensor)}
+        if self._eng is not None:
+            self._eng.load_state(self._state)
+        return self
+
+    def load_from_checkpoint(self, ckpt, map_location="cpu"):
+        """Lightning-style: returns the loaded model (eval_gsr_voicefixer.py:33 discards the receiver)."""
+        blob = torch.load(ckpt, map_location=map_location, weights_only=False)
+        sd = blob["state_dict"] if isinstance(blob, dict) and "state_dict" in blob else blob
+        self.load_state_dict(sd)
+        return self
+
+    def state_dict(self):
+        return dict(self._state or {})
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("inference-only engine: BatchNorm is folded in eval mode")
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("voicefixer_main_b200 has no CPU path; move the model to a CUDA device")
+        if self._eng is not None and self._eng.device == torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()):
+            return self
+        if self._eng is not None:
+            self._eng.close()
+        self._eng = Engine(device, self.voc_cfg)
+        self.device = self._eng.device
+        if self._state is not None:
+            self._eng.load_state(self._state)
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+
+    # ---- reference methods
+    def get_vocoder(self):
+        return self.vocoder
+
+    def get_f_helper(self):
+        return self.f_helper
+
+    def pre(self, input):
+        """gsr_voicefixer.py:178-181: input [B,1,N] -> (sp [B,1,T,1025], mel_orig [B,1,T,128])."""
+        sp = self.f_helper.wav_to_spectrogram(input)
+        mel_orig = self.mel(sp.permute(0, 1, 3, 2)).permute(0, 1, 3, 2)
+        return sp, mel_orig
+
+    def forward(self, mel_orig):
+        return self.generator(mel_orig)
+
+    def __call__(self, mel_orig):
+        return self.forward(mel_orig)
+
+    # ---- batched fused path
+    def restore(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """wav [B,N] fp32 on device -> restored [B,N]; one 60 s-or-shorter segment per row."""
+        return self._engine().restore(wav, out)
+
+    def restore_host(self, wav_host: torch.Tensor, out_host: torch.Tensor):
+        self._engine().restore_host(wav_host, out_host)
