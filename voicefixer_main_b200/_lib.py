@@ -17,7 +17,7 @@ EXPORTS = [
     "vf_default_config", "vf_create", "vf_destroy", "vf_last_error", "vf_load_weights", "vf_frontend",
     "vf_unet_mel", "vf_vocoder", "vf_vocoder_out_len", "vf_restore", "vf_restore_host", "vf_restore_stages",
     "vf_to_log", "vf_from_log", "vf_workspace_bytes", "vf_check_errors", "vf_set_option", "vf_launch_count",
-    "vf_enable_stage_timing", "vf_stage_times", "vf_selftest_gemm",
+    "vf_enable_stage_timing", "vf_stage_times", "vf_selftest_gemm", "vf_enable_op_timing", "vf_op_count", "vf_op_info",
 ]
 
 
@@ -83,6 +83,10 @@ def load_library():
     lib.vf_stage_times.argtypes = [P, POINTER(c_float * 4)]
     lib.vf_selftest_gemm.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_double),
                                      POINTER(c_double)]
+    lib.vf_enable_op_timing.argtypes = [P, c_int]
+    lib.vf_op_count.argtypes = [P]
+    lib.vf_op_info.argtypes = [P, c_int, POINTER(c_float), POINTER(c_double), POINTER(c_double), POINTER(c_int),
+                               POINTER(c_int), c_char_p, c_int]
     _lib = lib
     return lib
 

@@ -69,6 +69,8 @@ enum OpKind { OP_GEMM, OP_FIRST, OP_POOL, OP_COND, OP_REFLECT, OP_TAIL, OP_FINAL
 struct Op {
   OpKind kind;
   int bn = 0, bk = 0;
+  double flops = 0, bytes = 0;   // algorithmic work of this launch (reference op counts), for the roofline
+  char label[48] = {0};
   GemmTcParams tc;
   GemmSimtParams simt;
   UnetFirstParams first;
@@ -145,6 +147,10 @@ struct vf_ctx {
   float tail_b = 0;
   int voc_last_c = 64;
   std::map<std::pair<int, long>, std::unique_ptr<Plan>> plans;
+  bool op_timing = false;
+  struct ProfRec { std::string label; double flops, bytes; int bn, bk; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_ev;
   bool timing = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
@@ -444,6 +450,7 @@ struct Builder {
   vf_ctx* ctx;
   Plan* plan;
   int rc = VF_OK;
+  std::string label;   // name given to the next op (profiling only)
 
   template <typename T>
   T* alloc(size_t count) {
@@ -565,6 +572,20 @@ struct Builder {
       tp.stages = stages;
       tp.prob = pr;
     }
+    {   // algorithmic work: the reference op's own MAC count and the minimum HBM traffic of this launch
+      double kreal = 0, a_elems = 0;
+      for (auto& t : taps) kreal += std::min(t.nch, (t.src ? s1 : &s0)->pl.C);
+      const double wfrac = (epi.Wp > 1) ? double(epi.Wp - 1) / epi.Wp : 1.0;
+      double rows = (double)n_img * (epi.map == MAP_CONVT1D ? epi.rows_in - 1 : epi.rows_in) * wfrac;
+      op.flops = 2.0 * rows * N * kreal * (epi.map == MAP_CONVT2D ? 9.0 / 16.0 : 1.0);
+      a_elems += (double)n_img * s0.rows * s0.pl.C;
+      if (s1) a_elems += (double)n_img * s1->rows * s1->pl.C;
+      const double out_elems = (double)n_img * (epi.map == MAP_CONVT1D ? (double)epi.out_rows_valid * epi.cout
+                                                : (epi.map == MAP_CONVT2D ? 4.0 * epi.rows_in * epi.cout : (double)epi.rows_in * N));
+      op.bytes = a_elems * (terms == 3 ? 4 : 2) + (double)W.N * W.K * (terms == 3 ? 4 : 2) +
+                 out_elems * ((epi.out_raw ? 4 : 0) + (epi.out_r.hi ? 4 : 0) + (epi.out_a.hi ? 4 : 0) + (epi.resid ? 4 : 0));
+      snprintf(op.label, sizeof op.label, "%s", label.c_str());
+    }
     ops.push_back(op);
   }
 };
@@ -620,13 +641,16 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
       L.cat_a = b.planes(B, L.rows, 2 * L.C);
       L.P_r = b.planes(B, L.rows / 4, L.C);
       L.P_a = b.planes(B, L.rows / 4, L.C);
-      if (l == 5) L.P_raw = b.alloc<float>((size_t)B * (L.rows / 4) * L.C);
+      // the consumer of the pooled tensor needs it in fp32 when its shortcut is the identity (Cin == Cout)
+      if (l == 5 || !ctx->enc[l + 1][0].has_sc) L.P_raw = b.alloc<float>((size_t)B * (L.rows / 4) * L.C);
     }
   }
   if (b.rc) return b.rc;
 
+  std::string tag;   // profiling label of the block being emitted
   // conv1 of a block: A -> aT with the block's bn2 + LeakyReLU
   auto conv1 = [&](const ConvBlockW& w, Level& L, const Planes& in) {
+    b.label = tag + ".conv1";
     GemmEpilogue e = epi_plain(L.rows, L.Wp, w.cout, L.rows);
     set_out_a(e, L.aT, 0, w.bn2.scale, w.bn2.shift, ACT_LRELU, S);
     b.gemm(ops, w.conv1, ASrc{in, L.rows, 0}, nullptr, taps3x3(L.Wp, w.cin), e, B, terms);
@@ -642,6 +666,7 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
     }
     e.resid = resid;
     e.resid_ld = w.cout;
+    b.label = tag + (sc_src ? ".conv2+sc" : ".conv2");
     b.gemm(ops, w.conv2, ASrc{L.aT, L.rows, 0}, sc_src ? &s1 : nullptr, taps, e, B, terms);
   };
 
@@ -651,6 +676,7 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
     int cur = 0;   // raw[cur] holds the block input
     for (int j = 0; j < 4; ++j) {
       const ConvBlockW& w = ctx->enc[l][j];
+      tag = "enc" + std::to_string(l + 1) + ".b" + std::to_string(j + 1);
       const float* resid = nullptr;
       const Planes* sc = nullptr;
       if (j == 0 && l == 0) {
@@ -667,7 +693,8 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
         cur = 0;
       } else if (j == 0) {
         conv1(w, L, lv[l - 1].P_a);
-        sc = &lv[l - 1].P_r;
+        if (w.has_sc) sc = &lv[l - 1].P_r;
+        else resid = lv[l - 1].P_raw;      // encoder_block6: 384 -> 384, identity shortcut
         cur = 1;               // output goes to raw[0]
       } else {
         conv1(w, L, L.aX);
@@ -702,6 +729,7 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
   // ---------------- bottleneck (conv_block7, identity shortcut) -> decoder_block1.bn1 + ReLU
   {
     Level& L = lv[6];
+    tag = "bottleneck";
     conv1(ctx->bott, L, lv[5].P_a);
     GemmEpilogue e = epi_plain(L.rows, L.Wp, 384, L.rows);
     set_out_a(e, L.aX, 0, ctx->dec_bn1[0].scale, ctx->dec_bn1[0].shift, ACT_LRELU, 0.f);
@@ -723,11 +751,13 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
       std::vector<GemmTap> taps;
       for (int dh = 0; dh < 2; ++dh)
         for (int dw = 0; dw < 2; ++dw) taps.push_back(GemmTap{-(dh * Lin.Wp + dw), 0, 0, 0, cin});
+      b.label = "dec" + std::to_string(k + 1) + ".convT";
       b.gemm(ops, ctx->dec_up[k], ASrc{Lin.aX, Lin.rows, 0}, nullptr, taps, e, B, terms);
     }
     int cur = 0;
     for (int j = 0; j < 4; ++j) {
       const ConvBlockW& w = ctx->dec[k][j];
+      tag = "dec" + std::to_string(k + 1) + ".b" + std::to_string(j + 2);
       const float* resid = nullptr;
       const Planes* sc = nullptr;
       if (j == 0) { conv1(w, L, L.cat_a); sc = &L.cat_r; }
@@ -748,6 +778,7 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
       cur = dst;
     }
     if (k == 5) {   // after_conv_block1 + after_conv2 head + log-mel residual
+      tag = "post";
       conv1(ctx->post, L, L.aX);
       GemmEpilogue e = epi_plain(L.rows, L.Wp, 32, L.rows);
       e.head_w = ctx->d_head_w; e.head_b = ctx->head_b;
@@ -794,6 +825,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
     e.out_row0 = last ? 3 : 0;
     e.bias = ctx->voc_cond[i].bias;
     set_out_a(e, dst, 0, nullptr, nullptr, ACT_ELU, 0.f);
+    b.label = "voc.cond" + std::to_string(i);
     b.gemm(ops, ctx->voc_cond[i], ASrc{cur, Tv, 0}, nullptr, taps1d(3, 1, cur.C, true), e, B, terms);
     cur = dst;
   }
@@ -802,6 +834,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
     GemmEpilogue e = epi_plain(Tv, 0, c.voc_channels, Tv);
     e.bias = ctx->voc_stem.bias;
     set_out_a(e, stem, 0, nullptr, nullptr, ACT_LRELU, c.voc_stage_slope);
+    b.label = "voc.stem";
     b.gemm(ops, ctx->voc_stem, ASrc{cpad, Tv + 6, 0}, nullptr, taps1d(7, 1, CC, false), e, B, terms);
   }
   Planes prev = stem;
@@ -825,6 +858,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
       e.out_raw = xr[0]; e.raw_ld = cout;
       set_out_a(e, xa, 0, nullptr, nullptr, ACT_LRELU, c.voc_res_slope);
       std::vector<GemmTap> taps = {GemmTap{0, 0, 0, 0, cin}, GemmTap{-1, 0, 0, 0, cin}};
+      b.label = "voc.up" + std::to_string(s);
       b.gemm(ops, ctx->voc_up[s], ASrc{prev, (int)Lprev, 0}, nullptr, taps, e, B, terms);
     }
     int curx = 0;
@@ -836,6 +870,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         GemmEpilogue e = epi_plain((int)L, 0, cout, (int)L);
         e.bias = ctx->voc_res_a[s][i].bias;
         set_out_a(e, ha, 0, nullptr, nullptr, ACT_LRELU, c.voc_res_slope);
+        b.label = "voc.res" + std::to_string(s) + "." + std::to_string(i) + ".a";
         b.gemm(ops, ctx->voc_res_a[s][i], ASrc{xa, (int)L, 0}, nullptr, taps1d(3, dil, cout, true), e, B, terms);
       }
       {
@@ -846,6 +881,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         e.resid = xr[curx]; e.resid_ld = cout;
         if (!last) { e.out_raw = xr[1 - curx]; e.raw_ld = cout; }
         set_out_a(e, dst, 0, nullptr, nullptr, ACT_LRELU, last ? c.voc_stage_slope : c.voc_res_slope);
+        b.label = "voc.res" + std::to_string(s) + "." + std::to_string(i) + ".b";
         b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, nullptr, taps1d(3, 1, cout, true), e, B, terms);
         curx = 1 - curx;
       }
@@ -905,9 +941,26 @@ int ensure_io(vf_ctx* ctx, Plan* plan, long n) {
   return b.rc;
 }
 
+int prof_mark(vf_ctx* ctx, cudaStream_t st) {
+  const size_t i = ctx->prof.size();     // event i closes record i-1 and opens record i
+  while (ctx->prof_ev.size() <= i) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return fail(ctx, VF_ECUDA, "cudaEventCreate failed");
+    ctx->prof_ev.push_back(ev);
+  }
+  if (cudaEventRecord(ctx->prof_ev[i], st) != cudaSuccess) return fail(ctx, VF_ECUDA, "cudaEventRecord failed");
+  return VF_OK;
+}
+
 int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
   for (Op& op : ops) {
     cudaError_t e = cudaSuccess;
+    if (ctx->op_timing) {
+      int rc = prof_mark(ctx, st);
+      if (rc) return rc;
+      const char* kinds[] = {"gemm", "unet_first", "pool", "voc_condition", "reflect_fill", "voc_tail", "finalize", "memset"};
+      ctx->prof.push_back({op.label[0] ? std::string(op.label) : std::string(kinds[op.kind]), op.flops, op.bytes, op.bn, op.bk});
+    }
     switch (op.kind) {
       case OP_GEMM:
         e = ctx->validate_simt ? launch_gemm_simt(op.simt, st) : launch_gemm_tc(op.tc, op.bn, op.bk, st);
@@ -923,6 +976,7 @@ int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
     if (e != cudaSuccess) return fail(ctx, VF_ECUDA, "kernel launch (op kind %d): %s", (int)op.kind, cudaGetErrorString(e));
     ctx->launches++;
   }
+  if (ctx->op_timing) return prof_mark(ctx, st);   // closing event of the last record
   return VF_OK;
 }
 
@@ -1098,6 +1152,7 @@ VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float
   Plan* plan;
   rc = get_plan(ctx, batch, frames, &plan);
   if (rc) return rc;
+  if (ctx->op_timing) ctx->prof.clear();
   const bool tm = ctx->timing;
   if (tm) {
     for (auto& e : ctx->ev)
@@ -1232,6 +1287,31 @@ VF_API int vf_stage_times(vf_ctx* ctx, float ms[4]) {
   if (!ctx->ev_valid) return fail(ctx, VF_ESTATE, "no timed vf_restore yet");
   CK(cudaEventSynchronize(ctx->ev[4]));
   for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+  return VF_OK;
+}
+
+VF_API int vf_enable_op_timing(vf_ctx* ctx, int enable) {
+  if (!ctx) return VF_EINVAL;
+  ctx->op_timing = enable != 0;
+  ctx->prof.clear();
+  return VF_OK;
+}
+VF_API int vf_op_count(vf_ctx* ctx) { return ctx ? (int)ctx->prof.size() : -1; }
+VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, char* label, int label_cap) {
+  if (!ctx || i < 0 || i >= (int)ctx->prof.size()) return VF_EINVAL;
+  // records of the frontend / finalize launches are not tracked; record i spans events [i, i+1) except that
+  // each run_ops() call appends one closing event after its last op, so consecutive event pairs stay aligned
+  // only inside one call: look the pair up by walking the event list.
+  if ((size_t)i + 1 >= ctx->prof_ev.size()) return fail(ctx, VF_ESTATE, "no events recorded for op %d", i);
+  CK(cudaEventSynchronize(ctx->prof_ev[i + 1]));
+  float t = 0.f;
+  CK(cudaEventElapsedTime(&t, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+  if (ms) *ms = t;
+  if (flops) *flops = ctx->prof[i].flops;
+  if (bytes) *bytes = ctx->prof[i].bytes;
+  if (bn) *bn = ctx->prof[i].bn;
+  if (bk) *bk = ctx->prof[i].bk;
+  if (label && label_cap > 0) snprintf(label, label_cap, "%s", ctx->prof[i].label.c_str());
   return VF_OK;
 }
 

@@ -268,6 +268,22 @@ class Engine:
         self._ck(self.lib.vf_stage_times(self.ctx, ctypes.byref(arr)))
         return dict(zip(("frontend_ms", "unet_ms", "vocoder_ms", "tail_ms"), [float(x) for x in arr]))
 
+    def enable_op_timing(self, on: bool = True):
+        self._ck(self.lib.vf_enable_op_timing(self.ctx, int(on)))
+
+    def op_profile(self):
+        """Per-launch records of the last restore() run with op timing enabled."""
+        recs = []
+        buf = ctypes.create_string_buffer(64)
+        for i in range(self.lib.vf_op_count(self.ctx)):
+            ms, fl, by = ctypes.c_float(), ctypes.c_double(), ctypes.c_double()
+            bn, bk = ctypes.c_int(), ctypes.c_int()
+            self._ck(self.lib.vf_op_info(self.ctx, i, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by),
+                                         ctypes.byref(bn), ctypes.byref(bk), buf, 64))
+            recs.append({"label": buf.value.decode(), "ms": ms.value, "flops": fl.value, "bytes": by.value,
+                         "bn": bn.value, "bk": bk.value})
+        return recs
+
     def selftest_gemm(self, n_img, rows, cin, cout, ntaps, dilation=1, terms=3):
         d, r = ctypes.c_double(), ctypes.c_double()
         self._ck(self.lib.vf_selftest_gemm(self.ctx, n_img, rows, cin, cout, ntaps, dilation, terms,
