@@ -159,6 +159,22 @@ def test_restore_10s_golden_and_batch_invariance(model, golden_fingerprint_ok):
     assert torch.equal(again, out)                # deterministic
 
 
+def test_vocoder_single_term_mode_within_waveform_tolerance(model, golden_fingerprint_ok):
+    """hi-only fp16 operands for stage C (3x fewer MMAs, half the plane traffic): allowed only because the
+    waveform bar (1e-3 RMS) is far looser than the mel bar."""
+    g = load_golden("e2e_1s.npz")
+    eng = model._engine()
+    eng.set_option("vocoder_terms", 1)
+    try:
+        out = model.restore(torch.from_numpy(g["wav"]).cuda()).cpu()
+        eng.check_errors()
+    finally:
+        eng.set_option("vocoder_terms", 3)
+    rms = float((out - torch.from_numpy(g["out"])).pow(2).mean().sqrt())
+    print("e2e 1s, vocoder_terms=1: wav rms err", rms, "max", float((out - torch.from_numpy(g["out"])).abs().max()))
+    assert rms < WAV_RMS_TOL
+
+
 def test_handler_protocol_drop_in(model, state):
     """The exact call sequence of eval_gsr_voicefixer.py:51-72 on the mirror objects."""
     wav = O.synth_clips(1, 22050, seed=5)

@@ -503,6 +503,7 @@ struct Builder {
       if (t.nch % 64) bk = 32;
     // a short tail segment (the 32-channel shortcut of a 64-channel conv) may be zero-padded to BK = 64 when
     // the source has exactly that many channels: the TMA box then runs out of bounds and is zero-filled.
+    bool promoted = false;
     if (bk == 32) {
       bool main64 = true, padok = true;
       for (auto& t : taps) {
@@ -512,7 +513,13 @@ struct Builder {
           if (&t != &taps.back()) main64 = false;
         }
       }
-      if (main64 && padok && taps.size() > 1) bk = 64;
+      if (main64 && padok && taps.size() > 1) { bk = 64; promoted = true; }
+    }
+    // small-K layers are bound by loads/stores, not MMAs: narrower K chunks -> smaller stages -> 2-3 CTAs per SM
+    if (bk == 64 && !promoted) {
+      int ksum = 0;
+      for (auto& t : taps) ksum += t.nch;
+      if (ksum <= 1024) bk = 32;
     }
     const int N = W.N;
     const int bn = (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
@@ -567,9 +574,21 @@ struct Builder {
       const int stage = gemm_tc_stage_bytes(bn, bk);
       int total_chunks = 0;
       for (auto& t : taps) total_chunks += t.nch / bk;
-      int stages = std::min(bn == 128 ? 3 : 4, std::max(2, total_chunks));
-      while (stages > 2 && (size_t)stages * stage > 200 * 1024) --stages;
+      const int budget = (k <= 1024) ? 72 * 1024 : 200 * 1024;
+      int stages = std::max(2, std::min(std::min(total_chunks, 6), budget / stage));
       tp.stages = stages;
+      // accumulation chains (see gemm_tc.cu): keep truncating adds per accumulator <= ~64-72
+      const int ksteps = k / 16;
+      if (terms == 3 && ksteps * 3 > 64) {
+        tp.sep_corr = 1;
+        tp.n_main = ksteps > 96 ? 3 : 1;
+      } else {
+        tp.sep_corr = 0;
+        tp.n_main = 1;
+      }
+      int cols = 32;
+      while (cols < (tp.n_main + tp.sep_corr) * bn) cols *= 2;
+      tp.tmem_cols = cols;
       tp.prob = pr;
     }
     {   // algorithmic work: the reference op's own MAC count and the minimum HBM traffic of this launch

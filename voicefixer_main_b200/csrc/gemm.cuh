@@ -90,6 +90,9 @@ struct GemmTcParams {
   CUtensorMap a_hi[2], a_lo[2];   // [C, rows, n_img] fp16
   CUtensorMap b_hi, b_lo;         // [Ktot, N] fp16 (K-major)
   int stages;
+  int n_main;      // K loop dealt round-robin over this many TMEM accumulators (truncating adder: short chains)
+  int sep_corr;    // hi*lo + lo*hi accumulate in their own accumulator
+  int tmem_cols;   // power of two >= (n_main + sep_corr) * BN
   GemmProblem prob;
 };
 

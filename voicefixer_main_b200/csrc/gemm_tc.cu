@@ -3,39 +3,75 @@
 // One CTA = one 128 x BN output tile.  Warp roles (192 threads):
 //   warp 0 : TMA producer  - streams A (activation rows, shifted per tap) and B (packed weights) tiles
 //            into a `stages`-deep shared-memory ring (SWIZZLE_128B rows for BK = 64, SWIZZLE_64B for BK = 32)
-//   warp 1 : TMEM owner + single-thread tcgen05.mma issuer; accumulator 128 lanes x BN fp32 columns in TMEM
-//   warps 2-5 : epilogue - tcgen05.ld one TMEM lane (= output row) per thread, fused bias / residual /
-//            BN-affine / activation / hi-lo split / concat placement / 1x1 head, vectorised stores
-// Several CTAs co-reside per SM when the tile is small (BN = 32: 20 KB per stage, 32 TMEM columns), which
-// overlaps one CTA's epilogue with another's main loop.
+//   warp 1 : TMEM owner + single-thread tcgen05.mma issuer
+//   warps 2-5 : epilogue - one TMEM lane (= output row) per thread
+//
+// Accumulation precision.  The tensor core adds into its fp32 accumulator with truncation, so one long
+// chain of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with a single
+// accumulator).  The K loop is therefore dealt round-robin over `n_main` independent TMEM accumulators and
+// the two small correction products (hi*lo, lo*hi) go to their own accumulator; the epilogue sums them in
+// fp32 round-to-nearest.  This costs TMEM columns (<= 4 x BN of 512), not tensor throughput.
+//
+// Epilogue I/O.  A thread owns a row, but global accesses are issued row-major by the whole warp: values are
+// transposed through a swizzled shared-memory staging tile (aliasing pipeline stage 0, idle by then) so every
+// LDG/STG instruction touches whole 64/128-byte row segments.  Per-tile constants (bias, BN scale/shift, head
+// weights) are staged in shared memory once.  Small tiles co-reside 2-3 CTAs per SM so one CTA's epilogue
+// overlaps another's loads and MMAs.
 #include "gemm.cuh"
 #include "ptx.cuh"
 
 namespace vf {
 
+namespace {
+
+constexpr int kRowValid = 1, kRowPad = 2;
+
+struct RowInfo {        // published per epilogue thread for its own row, read by the lanes that store that row
+  uint32_t orow;        // output row index (already includes image base / row0 / phase mapping)
+  uint32_t flags;
+};
+
+// 32 rows x 128 B staging tile (fp32 x 32 columns): 16-byte column index is XOR-swizzled with the row.
+__device__ __forceinline__ int sw128(int row, int c16) { return row * 8 + (c16 ^ (row & 7)); }
+// 32 rows x 64 B staging tile (fp16 x 32 columns)
+__device__ __forceinline__ int sw64(int row, int c16) { return row * 4 + (c16 ^ ((row >> 1) & 3)); }
+
+}  // namespace
+
 template <int BN, int BK>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
+__global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
   constexpr int A_BYTES = GEMM_BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   constexpr int ROW_BYTES = BK * 2;
   constexpr int KSTEPS = BK / 16;
+  static_assert(2 * STAGE_BYTES >= 4 * 4096 + 4 * 2 * 2048, "staging must fit in two pipeline stages");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = P.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  uint8_t* tail = smem + (size_t)stages * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);   // [BN]
+  float* s_scale = s_bias + BN;                                // [BN]
+  float* s_shift = s_scale + BN;                               // [BN]
+  float* s_head = s_shift + BN;                                // [32]
+  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_head + 32);   // [128]
 
   const GemmProblem& pr = P.prob;
+  const GemmEpilogue& e = pr.epi;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int img = blockIdx.x / pr.m_tiles;
   const int m0 = (blockIdx.x - img * pr.m_tiles) * GEMM_BM;
   const int n0 = blockIdx.y * BN;
   const bool three = pr.terms == 3;
+  const int n_main = P.n_main;
+  const bool sep_corr = P.sep_corr != 0;
+  const int n_acc = n_main + (sep_corr ? 1 : 0);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -51,7 +87,18 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Ge
       tma_prefetch_desc(&P.b_lo);
     }
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_holder);
+  if (warp == 1) tmem_alloc_dyn(tmem_holder, P.tmem_cols);
+  if (warp >= 2) {   // per-tile constants
+    const int i = threadIdx.x - 64;
+    if (i < BN) {
+      s_bias[i] = e.bias ? __ldg(e.bias + n0 + i) : 0.f;
+      int co = n0 + i;
+      if (e.map != MAP_PLAIN) co -= (co / e.cout) * e.cout;
+      s_scale[i] = e.a_scale ? __ldg(e.a_scale + co) : 1.f;
+      s_shift[i] = e.a_scale ? __ldg(e.a_shift + co) : 0.f;
+    }
+    if (i < 32) s_head[i] = e.head_w ? __ldg(e.head_w + i) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -67,7 +114,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Ge
         for (int c = 0; c < tap.nch; c += BK, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1;
-          if (!mbar_wait(empty_bar + s, ph ^ 1, pr.epi.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+          if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           mbar_expect_tx(full_bar + s, tx_bytes);
           tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
@@ -84,61 +131,216 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Ge
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
       int it = 0;
+      uint32_t started = 0;     // bit a: accumulator a has been written
       bool ok = true;
       for (int t = 0; t < pr.ntaps && ok; ++t) {
         const int nch = pr.taps[t].nch;
         for (int c = 0; c < nch; c += BK, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1;
-          if (!mbar_wait(full_bar + s, ph, pr.epi.err, ERR_PIPE_MMA)) { ok = false; break; }
+          if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint32_t a_lo = a_hi + A_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_BYTES;
           const uint32_t b_lo = b_hi + B_BYTES;
+          const int am = it % n_main;
+          const int ac = sep_corr ? n_main : am;
+          const uint32_t d_main = tmem_base + am * BN;
+          const uint32_t d_corr = tmem_base + ac * BN;
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k) {
             const uint64_t da_hi = make_smem_desc(a_hi + k * 32, ROW_BYTES);
             const uint64_t db_hi = make_smem_desc(b_hi + k * 32, ROW_BYTES);
-            umma_f16(tmem_base, da_hi, db_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_f16(d_main, da_hi, db_hi, idesc, (started >> am) & 1u);
+            started |= 1u << am;
             if (three) {
-              umma_f16(tmem_base, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, 1u);
-              umma_f16(tmem_base, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
+              umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, (started >> ac) & 1u);
+              started |= 1u << ac;
+              umma_f16(d_corr, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
             }
           }
           umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
         }
       }
-      umma_commit(tmem_full_bar);       // accumulator complete
+      umma_commit(tmem_full_bar);       // all accumulators complete
     }
     __syncwarp();
   } else {
+    // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int r = m0 + q * 32 + lane;
-    if (mbar_wait(tmem_full_bar, 0, pr.epi.err, ERR_PIPE_EPILOGUE)) {
+    const int rt = q * 32 + lane;       // row inside the tile
+    const int r = m0 + rt;              // GEMM row inside the image
+    const bool row_ok = r < e.rows_in;
+    if (mbar_wait(tmem_full_bar, 0, e.err, ERR_PIPE_EPILOGUE)) {
       tc_fence_after();
+      // staging (aliases pipeline stages 0-1: every MMA that read them has completed)
+      float4* stg_f = reinterpret_cast<float4*>(smem) + (size_t)q * 256;                 // 4 KB per warp
+      uint4* stg_h = reinterpret_cast<uint4*>(smem + 16384) + (size_t)q * 256;           // 2 x 2 KB per warp
+      uint4* stg_l = stg_h + 128;
+      RowInfo* rows = s_rows + q * 32;
       float head_acc = 0.f;
+      bool ovf = false;
+      const bool pad_plain = (e.map == MAP_PLAIN) && e.Wp > 0 && (r % e.Wp) == e.Wp - 1;
+      int cth = 0, ctw = 0;
+      if (e.map == MAP_CONVT2D) { cth = r / e.Wp; ctw = r - cth * e.Wp; }
+
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
+        const int nb = n0 + j * 32;
+        // ---- accumulators -> registers, summed in fp32 round-to-nearest
         float v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 32, v);
-        epilogue_chunk(pr.epi, img, r, n0 + j * 32, v, head_acc);
+        for (int a = 1; a < n_acc; ++a) {
+          float w[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + j * 32, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+        }
+        // ---- row mapping for this column chunk
+        int co0 = nb, phase = 0;
+        if (e.map != MAP_PLAIN) { phase = nb / e.cout; co0 = nb - phase * e.cout; }
+        uint32_t orow = 0, flags = 0;
+        if (row_ok) {
+          if (e.map == MAP_PLAIN) {
+            orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + r);
+            flags = kRowValid | (pad_plain ? kRowPad : 0);
+          } else if (e.map == MAP_CONVT2D) {
+            const int ph = phase >> 1, pw = phase & 1;
+            orow = (uint32_t)((size_t)img * e.out_img_rows + (size_t)(2 * cth + ph) * (2 * e.Wp) + 2 * ctw + pw);
+            flags = kRowValid | ((ctw == e.Wp - 1 && pw == 1) ? kRowPad : 0);
+          } else {
+            const long t = (long)r * e.ct_stride + phase - e.ct_pad;
+            if (t >= 0 && t < e.out_rows_valid) {
+              orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + t);
+              flags = kRowValid;
+            }
+          }
+        }
+        __syncwarp();
+        rows[lane] = RowInfo{orow, flags};
+        // ---- bias
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += s_bias[j * 32 + i];
+        // ---- residual: coalesced global -> staging -> own row
+        if (e.resid) {
+          const size_t rbase = ((size_t)img * e.rows_in + m0 + q * 32) * e.resid_ld + co0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), c16 = lane & 7;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + q * 32 + rr < e.rows_in)
+              x = __ldg(reinterpret_cast<const float4*>(e.resid + rbase + (size_t)rr * e.resid_ld) + c16);
+            stg_f[sw128(rr, c16)] = x;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = stg_f[sw128(lane, i)];
+            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          }
+        }
+        const bool pad = (flags & kRowPad) != 0;
+        if (pad) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        // ---- fp32 output
+        if (e.out_raw) {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) stg_f[sw128(lane, i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), c16 = lane & 7;
+            const RowInfo ri = rows[rr];
+            if (ri.flags & kRowValid)
+              reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[c16] = stg_f[sw128(rr, c16)];
+          }
+        }
+        // ---- raw hi/lo planes
+        if (e.out_r.hi) {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __align__(16) __half h[8];
+            __align__(16) __half l[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              h[k] = __float2half_rn(v[8 * i + k]);
+              l[k] = __float2half_rn(v[8 * i + k] - __half2float(h[k]));
+            }
+            stg_h[sw64(lane, i)] = *reinterpret_cast<const uint4*>(h);
+            stg_l[sw64(lane, i)] = *reinterpret_cast<const uint4*>(l);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2), c16 = lane & 3;
+            const RowInfo ri = rows[rr];
+            if (ri.flags & kRowValid) {
+              const size_t o = (size_t)ri.orow * e.out_r.ld + e.out_r.c_off + co0;
+              reinterpret_cast<uint4*>(e.out_r.hi + o)[c16] = stg_h[sw64(rr, c16)];
+              reinterpret_cast<uint4*>(e.out_r.lo + o)[c16] = stg_l[sw64(rr, c16)];
+            }
+          }
+        }
+        // ---- fused 1x1 head (N == 32)
+        if (e.head_w) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) head_acc = fmaf(v[i], s_head[i], head_acc);
+        }
+        // ---- activated hi/lo planes (consumer's BN affine + activation)
+        if (e.out_a.hi) {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __align__(16) __half h[8];
+            __align__(16) __half l[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int cidx = j * 32 + 8 * i + k;
+              float a = fmaf(v[8 * i + k], s_scale[cidx], s_shift[cidx]);
+              if (e.act == ACT_LRELU) a = a > 0.f ? a : a * e.slope;
+              else if (e.act == ACT_ELU) a = a > 0.f ? a : expm1f(a);
+              if (pad) a = 0.f;
+              ovf |= !(fabsf(a) <= 65504.f);
+              h[k] = __float2half_rn(a);
+              l[k] = __float2half_rn(a - __half2float(h[k]));
+            }
+            stg_h[sw64(lane, i)] = *reinterpret_cast<const uint4*>(h);
+            stg_l[sw64(lane, i)] = *reinterpret_cast<const uint4*>(l);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2), c16 = lane & 3;
+            const RowInfo ri = rows[rr];
+            if (ri.flags & kRowValid) {
+              const size_t o = (size_t)ri.orow * e.out_a.ld + e.out_a.c_off + co0;
+              reinterpret_cast<uint4*>(e.out_a.hi + o)[c16] = stg_h[sw64(rr, c16)];
+              if (three) reinterpret_cast<uint4*>(e.out_a.lo + o)[c16] = stg_l[sw64(rr, c16)];
+            }
+          }
+        }
       }
-      epilogue_head(pr.epi, img, r, head_acc);
+      if (ovf && row_ok && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
+      epilogue_head(e, img, r, head_acc);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc_dyn(tmem_base, P.tmem_cols);
   }
 }
 
 template <int BN, int BK>
 static cudaError_t launch_one(const GemmTcParams& p, cudaStream_t stream) {
   constexpr int STAGE_BYTES = 2 * (GEMM_BM * BK * 2 + BN * BK * 2);
-  const size_t smem = (size_t)p.stages * STAGE_BYTES + (2 * p.stages + 1) * 8 + 16 + 1024;
+  const size_t smem = (size_t)p.stages * STAGE_BYTES + (2 * p.stages + 1) * 8 + 16 + (3 * BN + 32) * 4 + 128 * 8 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
