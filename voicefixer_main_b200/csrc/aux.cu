@@ -186,52 +186,79 @@ cudaError_t launch_reflect_fill(PlanePtr planes, int batch, int L, int C, int pa
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) voc_tail_kernel(VocTailParams p) {
-  extern __shared__ float w_s[];                                          // [7][C]
-  for (int i = threadIdx.x; i < 7 * p.C; i += blockDim.x) w_s[i] = p.w[i];
-  __syncthreads();
+// Tile = 128 output samples of one clip.  The 134 x C input rows are staged once in shared memory as fp32
+// (coalesced 16-byte loads of the hi / lo planes), then every thread accumulates its 7 x C taps from smem:
+// the 7-fold row reuse never goes back to L1/L2.  Row pitch C + 4 floats keeps the float4 reads conflict-free.
+constexpr int TAIL_TILE = 128;
+__global__ void __launch_bounds__(TAIL_TILE) voc_tail_kernel(VocTailParams p) {
+  extern __shared__ float tail_smem[];
+  const int C = p.C, pitch = C + 4;
+  float* w_s = tail_smem;                       // [7][C]
+  float* x_s = tail_smem + 7 * C;               // [TAIL_TILE + 6][pitch]
   const int b = blockIdx.y;
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long t0 = (long)blockIdx.x * TAIL_TILE;
+  const size_t rows = (size_t)p.L + 6;
+  const int nrows = (int)min((long)TAIL_TILE + 6, (long)rows - t0);
+  for (int i = threadIdx.x; i < 7 * C; i += TAIL_TILE) w_s[i] = __ldg(p.w + i);
+  const int cg = C / 8;
+  for (int idx = threadIdx.x; idx < nrows * cg; idx += TAIL_TILE) {
+    const int rr = idx / cg, g = idx - rr * cg;
+    const size_t off = ((size_t)b * rows + t0 + rr) * C + g * 8;
+    const uint4 hq = __ldg(reinterpret_cast<const uint4*>(p.in.hi + off));
+    const __half* h = reinterpret_cast<const __half*>(&hq);
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = __half2float(h[i]);
+    if (p.terms == 3) {
+      const uint4 lq = __ldg(reinterpret_cast<const uint4*>(p.in.lo + off));
+      const __half* l = reinterpret_cast<const __half*>(&lq);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += __half2float(l[i]);
+    }
+    float4* dst = reinterpret_cast<float4*>(x_s + rr * pitch + g * 8);
+    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+  }
+  __syncthreads();
+  const long t = t0 + threadIdx.x;
   float mag = 0.f;
   if (t < p.L) {
-    float acc = p.bias;
-    const size_t rows = (size_t)p.L + 6;
+    float acc0 = p.bias, acc1 = 0.f;
     for (int k = 0; k < 7; ++k) {
-      const size_t base = ((size_t)b * rows + t + k) * p.C;
-      for (int c = 0; c < p.C; c += 8) {
-        const uint4 hq = __ldg(reinterpret_cast<const uint4*>(p.in.hi + base + c));
-        const __half* h = reinterpret_cast<const __half*>(&hq);
-        float a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = __half2float(h[i]);
-        if (p.terms == 3) {
-          const uint4 lq = __ldg(reinterpret_cast<const uint4*>(p.in.lo + base + c));
-          const __half* l = reinterpret_cast<const __half*>(&lq);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a[i] += __half2float(l[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(a[i], w_s[k * p.C + c + i], acc);
+      const float4* xr = reinterpret_cast<const float4*>(x_s + (threadIdx.x + k) * pitch);
+      const float4* wr = reinterpret_cast<const float4*>(w_s + k * C);
+#pragma unroll 4
+      for (int c = 0; c < C / 4; c += 2) {
+        const float4 x0 = xr[c], x1 = xr[c + 1], w0 = wr[c], w1 = wr[c + 1];
+        acc0 = fmaf(x0.x, w0.x, acc0); acc0 = fmaf(x0.y, w0.y, acc0); acc0 = fmaf(x0.z, w0.z, acc0); acc0 = fmaf(x0.w, w0.w, acc0);
+        acc1 = fmaf(x1.x, w1.x, acc1); acc1 = fmaf(x1.y, w1.y, acc1); acc1 = fmaf(x1.z, w1.z, acc1); acc1 = fmaf(x1.w, w1.w, acc1);
       }
     }
-    const float y = tanhf(acc);
+    const float y = tanhf(acc0 + acc1);
     p.wav[(size_t)b * p.L + t] = y;
     mag = fabsf(y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, o));
-  __shared__ float wmax[8];
+  __shared__ float wmax[TAIL_TILE / 32];
   if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mag;
   __syncthreads();
   if (threadIdx.x == 0) {
     float m = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, wmax[i]);
+    for (int i = 0; i < TAIL_TILE / 32; ++i) m = fmaxf(m, wmax[i]);
     atomicMax(p.peak_bits + b, __float_as_uint(m));
   }
 }
 cudaError_t launch_voc_tail(const VocTailParams& p, cudaStream_t stream) {
-  dim3 grid((unsigned)((p.L + 255) / 256), p.batch);
-  voc_tail_kernel<<<grid, 256, 7 * p.C * sizeof(float), stream>>>(p);
+  dim3 grid((unsigned)((p.L + TAIL_TILE - 1) / TAIL_TILE), p.batch);
+  const size_t smem = (size_t)(7 * p.C + (TAIL_TILE + 6) * (p.C + 4)) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(voc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  voc_tail_kernel<<<grid, TAIL_TILE, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -118,7 +118,7 @@ struct vf_ctx {
   size_t weight_bytes = 0;
   bool loaded = false;
   EncodeTiledFn encode = nullptr;
-  int unet_terms = 3, voc_terms = 3, validate_simt = 0;
+  int unet_terms = 3, voc_terms = 1, validate_simt = 0;
   int64_t launches = 0;
   int* d_err = nullptr;      // [0] device error code, [1] negative-input count
   // tables
@@ -279,14 +279,17 @@ int pack_convT2d(vf_ctx* ctx, GemmW* out, const HostT& w) {
   return upload_gemm(ctx, out, m, N, K, nullptr);
 }
 
-// Conv1d [Cout][Cin][k] -> [Cout][k*Cin]
-int pack_conv1d(vf_ctx* ctx, GemmW* out, const HostT& w, const HostT& b) {
+// Conv1d [Cout][Cin][k] -> [Cout][k*Cin (+ Cout)]; with `identity` an identity block is appended so the
+// residual stream x (kept as fp16 hi/lo planes) is added inside the same accumulator: x' = x + conv(...)
+int pack_conv1d(vf_ctx* ctx, GemmW* out, const HostT& w, const HostT& b, bool identity = false) {
   const int cout = (int)w.shape[0], cin = (int)w.shape[1], k = (int)w.shape[2];
-  const int K = k * cin;
-  std::vector<float> m((size_t)cout * K);
-  for (int n = 0; n < cout; ++n)
+  const int K = k * cin + (identity ? cout : 0);
+  std::vector<float> m((size_t)cout * K, 0.f);
+  for (int n = 0; n < cout; ++n) {
     for (int c = 0; c < cin; ++c)
       for (int t = 0; t < k; ++t) m[(size_t)n * K + t * cin + c] = w.v[((size_t)n * cin + c) * k + t];
+    if (identity) m[(size_t)n * K + k * cin + n] = 1.f;
+  }
   return upload_gemm(ctx, out, m, cout, K, &b.v);
 }
 
@@ -428,7 +431,7 @@ int load_all(vf_ctx* ctx) {
       const std::string p = "vocoder.res." + std::to_string(s) + "." + std::to_string(i);
       NEED(wa, p + ".a.weight"); NEED(ba, p + ".a.bias"); NEED(wb, p + ".b.weight"); NEED(bb, p + ".b.bias");
       rc = pack_conv1d(ctx, &ctx->voc_res_a[s][i], *wa, *ba); if (rc) return rc;
-      rc = pack_conv1d(ctx, &ctx->voc_res_b[s][i], *wb, *bb); if (rc) return rc;
+      rc = pack_conv1d(ctx, &ctx->voc_res_b[s][i], *wb, *bb, true); if (rc) return rc;
     }
   }
   {
@@ -593,7 +596,7 @@ struct Builder {
     }
     {   // algorithmic work: the reference op's own MAC count and the minimum HBM traffic of this launch
       double kreal = 0, a_elems = 0;
-      for (auto& t : taps) kreal += std::min(t.nch, (t.src ? s1 : &s0)->pl.C);
+      for (auto& t : taps) if (!t.both) kreal += std::min(t.nch, (t.src ? s1 : &s0)->pl.C);
       const double wfrac = (epi.Wp > 1) ? double(epi.Wp - 1) / epi.Wp : 1.0;
       double rows = (double)n_img * (epi.map == MAP_CONVT1D ? epi.rows_in - 1 : epi.rows_in) * wfrac;
       op.flops = 2.0 * rows * N * kreal * (epi.map == MAP_CONVT2D ? 9.0 / 16.0 : 1.0);
@@ -863,7 +866,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
     const int sc = c.voc_scales[s], cout = cin / 2;
     const long L = Lprev * sc;
     const bool last_stage = s == c.voc_num_stages - 1;
-    float* xr[2] = {b.alloc<float>((size_t)B * L * cout), b.alloc<float>((size_t)B * L * cout)};
+    Planes xr[2] = {b.planes(B, (int)L, cout), b.planes(B, (int)L, cout)};   // residual stream x as hi/lo planes
     Planes xa = b.planes(B, (int)L, cout), ha = b.planes(B, (int)L, cout);
     Planes tail_in;
     if (last_stage) tail_in = b.planes(B, (int)L + 6, cout);
@@ -874,7 +877,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
       e.map = MAP_CONVT1D; e.rows_in = (int)Lprev + 1; e.cout = cout; e.out_img_rows = (int)L; e.out_rows_valid = (int)L;
       e.ct_stride = sc; e.ct_pad = sc / 2 + sc % 2;
       e.bias = ctx->voc_up[s].bias;
-      e.out_raw = xr[0]; e.raw_ld = cout;
+      e.out_r = OutPlane{xr[0].p.hi, xr[0].p.lo, cout, 0};
       set_out_a(e, xa, 0, nullptr, nullptr, ACT_LRELU, c.voc_res_slope);
       std::vector<GemmTap> taps = {GemmTap{0, 0, 0, 0, cin}, GemmTap{-1, 0, 0, 0, cin}};
       b.label = "voc.up" + std::to_string(s);
@@ -897,11 +900,13 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         GemmEpilogue e = epi_plain((int)L, 0, cout, dst.img_rows);
         e.out_row0 = (last && last_stage) ? 3 : 0;
         e.bias = ctx->voc_res_b[s][i].bias;
-        e.resid = xr[curx]; e.resid_ld = cout;
-        if (!last) { e.out_raw = xr[1 - curx]; e.raw_ld = cout; }
+        if (!last) e.out_r = OutPlane{xr[1 - curx].p.hi, xr[1 - curx].p.lo, cout, 0};
         set_out_a(e, dst, 0, nullptr, nullptr, ACT_LRELU, last ? c.voc_stage_slope : c.voc_res_slope);
         b.label = "voc.res" + std::to_string(s) + "." + std::to_string(i) + ".b";
-        b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, nullptr, taps1d(3, 1, cout, true), e, B, terms);
+        std::vector<GemmTap> taps = taps1d(3, 1, cout, true);
+        taps.push_back(GemmTap{0, 1, 0, 0, cout, 1});          // x itself: identity weights, both planes
+        ASrc xsrc{xr[curx], (int)L, 0};
+        b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, &xsrc, taps, e, B, terms);
         curx = 1 - curx;
       }
     }

@@ -39,6 +39,8 @@ struct GemmTap {
   int c_off;   // first channel inside the source
   int k_off;   // first column of this tap's segment in the packed weight matrix
   int nch;     // channels contracted by this tap (multiple of the kernel's BK)
+  int both;    // 1: contract hi AND lo planes of A even in 1-term mode (identity tap carrying the fp32-grade
+               //    residual stream through the accumulator)
 };
 
 struct OutPlane {

@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = (three ? 2u : 1u) * (A_BYTES + B_BYTES);
       int it = 0;
       bool ok = true;
       for (int t = 0; t < pr.ntaps && ok; ++t) {
@@ -116,13 +115,12 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
           const uint32_t ph = (it / stages) & 1;
           if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-          mbar_expect_tx(full_bar + s, tx_bytes);
+          const bool a_lo = three || tap.both;
+          mbar_expect_tx(full_bar + s, (a_lo ? 2u : 1u) * A_BYTES + (three ? 2u : 1u) * B_BYTES);
           tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
           tma_load_2d(st + 2 * A_BYTES, &P.b_hi, full_bar + s, tap.k_off + c, n0);
-          if (three) {
-            tma_load_3d(st + A_BYTES, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
-          }
+          if (a_lo) tma_load_3d(st + A_BYTES, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
+          if (three) tma_load_2d(st + 2 * A_BYTES + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
         }
       }
     }
@@ -135,6 +133,7 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
       bool ok = true;
       for (int t = 0; t < pr.ntaps && ok; ++t) {
         const int nch = pr.taps[t].nch;
+        const bool both = pr.taps[t].both != 0;
         for (int c = 0; c < nch; c += BK, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1;
@@ -158,6 +157,8 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
               umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, (started >> ac) & 1u);
               started |= 1u << ac;
               umma_f16(d_corr, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
+            } else if (both) {
+              umma_f16(d_main, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
             }
           }
           umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
