@@ -24,7 +24,7 @@
 
 namespace vf {
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
-int gemm_tc_stage_bytes(int bn, int bk);
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms);
 cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
 }  // namespace vf
 
@@ -118,6 +118,7 @@ struct vf_ctx {
   size_t weight_bytes = 0;
   bool loaded = false;
   EncodeTiledFn encode = nullptr;
+  int sm_count = 148;
   int unet_terms = 3, voc_terms = 1, validate_simt = 0;
   int64_t launches = 0;
   int* d_err = nullptr;      // [0] device error code, [1] negative-input count
@@ -574,12 +575,6 @@ struct Builder {
       }
       if (!rc) rc = make_map2(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
       if (!rc) rc = make_map2(&tp.b_lo, W.lo, W.K, N, bk, bn, bk == 64);
-      const int stage = gemm_tc_stage_bytes(bn, bk);
-      int total_chunks = 0;
-      for (auto& t : taps) total_chunks += t.nch / bk;
-      const int budget = (k <= 1024) ? 72 * 1024 : 200 * 1024;
-      int stages = std::max(2, std::min(std::min(total_chunks, 6), budget / stage));
-      tp.stages = stages;
       // accumulation chains (see gemm_tc.cu): keep truncating adds per accumulator <= ~64-72
       const int ksteps = k / 16;
       if (terms == 3 && ksteps * 3 > 64) {
@@ -589,9 +584,28 @@ struct Builder {
         tp.sep_corr = 0;
         tp.n_main = 1;
       }
-      int cols = 32;
-      while (cols < (tp.n_main + tp.sep_corr) * bn) cols *= 2;
-      tp.tmem_cols = cols;
+      const int n_acc = tp.n_main + tp.sep_corr;
+      bool any_both = false;
+      for (auto& t : taps) any_both |= t.both != 0;
+      tp.planes_a = (terms == 3 || any_both) ? 2 : 1;
+      auto pow2 = [](int x) { int c = 32; while (c < x) c *= 2; return c; };
+      // occupancy: small-K tiles are bound by loads/stores -> several persistent CTAs per SM; large-K -> one
+      const int reg_limit = bn == 32 ? 3 : (bn == 64 ? 2 : 1);
+      int ctas = (k <= 1024) ? reg_limit : 1;
+      int stages = 0;
+      for (; ctas >= 1; --ctas) {
+        tp.acc_bufs = (pow2(2 * n_acc * bn) * ctas <= 512) ? 2 : 1;
+        tp.tmem_cols = pow2(tp.acc_bufs * n_acc * bn);
+        if (tp.tmem_cols * ctas > 512) continue;
+        const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
+        for (stages = 8; stages >= 2; --stages)
+          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms) <= per_cta) break;
+        if (stages >= 2) break;
+      }
+      if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d n_acc=%d)", bn, bk, n_acc); return; }
+      tp.stages = stages;
+      const long total_tiles = (long)n_img * pr.m_tiles * (N / bn);
+      tp.grid = (int)std::min<long>(total_tiles, (long)ctx->sm_count * ctas);
       tp.prob = pr;
     }
     {   // algorithmic work: the reference op's own MAC count and the minimum HBM traffic of this launch
@@ -1072,6 +1086,7 @@ VF_API int vf_create(vf_ctx** out, int device, const vf_config* cfg) {
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   if (e != cudaSuccess || !fn) return fail(nullptr, VF_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   ctx->encode = (EncodeTiledFn)fn;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   vf_ctx* raw = ctx.get();
   size_t acct = 0;
   int rc = dev_alloc(raw, raw->allocs, acct, &raw->d_err, 4);

@@ -94,7 +94,10 @@ struct GemmTcParams {
   int stages;
   int n_main;      // K loop dealt round-robin over this many TMEM accumulators (truncating adder: short chains)
   int sep_corr;    // hi*lo + lo*hi accumulate in their own accumulator
-  int tmem_cols;   // power of two >= (n_main + sep_corr) * BN
+  int tmem_cols;   // power of two >= acc_bufs * (n_main + sep_corr) * BN
+  int acc_bufs;    // 2: accumulator set double buffered in TMEM (epilogue of tile i overlaps MMAs of tile i+1)
+  int planes_a;    // smem slots per stage for A: 2 when any tap contracts the lo plane
+  int grid;        // persistent CTAs
   GemmProblem prob;
 };
 

@@ -1,22 +1,24 @@
 // tcgen05 implementation of the flat-shift multi-tap GEMM (see gemm.cuh).
 //
-// One CTA = one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0 : TMA producer  - streams A (activation rows, shifted per tap) and B (packed weights) tiles
-//            into a `stages`-deep shared-memory ring (SWIZZLE_128B rows for BK = 64, SWIZZLE_64B for BK = 32)
-//   warp 1 : TMEM owner + single-thread tcgen05.mma issuer
-//   warps 2-5 : epilogue - one TMEM lane (= output row) per thread
+// Persistent, warp-specialised: each CTA loops over 128 x BN output tiles (tile = blockIdx.x + i * gridDim.x,
+// N tiles of one M tile adjacent so co-running CTAs share the A rows in L2).
+//   warp 0     : TMA producer - streams A (activation rows, shifted per tap) and B (packed weights) tiles into a
+//                `stages`-deep shared-memory ring that runs ahead across tile boundaries
+//                (SWIZZLE_128B rows for BK = 64, SWIZZLE_64B for BK = 32)
+//   warp 1     : TMEM owner + single-thread tcgen05.mma issuer; the accumulator set is double buffered in TMEM
+//                when it fits, so tile i+1 accumulates while tile i drains
+//   warps 2..  : epilogue (4 or 8 warps; one TMEM lane = output row per thread, two warps share a lane quarter
+//                and split the column chunks)
 //
-// Accumulation precision.  The tensor core adds into its fp32 accumulator with truncation, so one long
-// chain of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with a single
-// accumulator).  The K loop is therefore dealt round-robin over `n_main` independent TMEM accumulators and
-// the two small correction products (hi*lo, lo*hi) go to their own accumulator; the epilogue sums them in
-// fp32 round-to-nearest.  This costs TMEM columns (<= 4 x BN of 512), not tensor throughput.
+// Accumulation precision.  The tensor core adds into its fp32 accumulator with truncation, so one long chain
+// of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with one accumulator).
+// The K loop is therefore dealt round-robin over `n_main` independent TMEM accumulators and the two small
+// correction products (hi*lo, lo*hi) go to their own accumulator; the epilogue sums them in fp32
+// round-to-nearest.  This costs TMEM columns, not tensor throughput.
 //
-// Epilogue I/O.  A thread owns a row, but global accesses are issued row-major by the whole warp: values are
-// transposed through a swizzled shared-memory staging tile (aliasing pipeline stage 0, idle by then) so every
-// LDG/STG instruction touches whole 64/128-byte row segments.  Per-tile constants (bias, BN scale/shift, head
-// weights) are staged in shared memory once.  Small tiles co-reside 2-3 CTAs per SM so one CTA's epilogue
-// overlaps another's loads and MMAs.
+// Epilogue I/O.  A thread owns a row, but global stores are issued row-major by the whole warp: values are
+// transposed through a swizzled shared-memory staging tile so every LDG/STG instruction touches whole
+// 64/128-byte row segments.  Per-tile constants (bias, BN scale/shift, head weights) live in shared memory.
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -36,49 +38,61 @@ __device__ __forceinline__ int sw128(int row, int c16) { return row * 8 + (c16 ^
 // 32 rows x 64 B staging tile (fp16 x 32 columns)
 __device__ __forceinline__ int sw64(int row, int c16) { return row * 4 + (c16 ^ ((row >> 1) & 3)); }
 
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
 }  // namespace
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
+template <int BN, int BK, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64 ? 2 : 1)))
+    gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
   constexpr int A_BYTES = GEMM_BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   constexpr int ROW_BYTES = BK * 2;
   constexpr int KSTEPS = BK / 16;
-  static_assert(2 * STAGE_BYTES >= 4 * 4096 + 4 * 2 * 2048, "staging must fit in two pipeline stages");
+  constexpr int EPI_THREADS = 32 * EPI_WARPS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = P.stages;
-  uint8_t* tail = smem + (size_t)stages * STAGE_BYTES;
+  const bool three = P.prob.terms == 3;
+  const int planes_a = P.planes_a;                      // 2 when any tap contracts the lo plane of A
+  const int stage_bytes = planes_a * A_BYTES + (three ? 2 : 1) * B_BYTES;
+  const int off_b = planes_a * A_BYTES;
+  uint8_t* stg_base = smem + (size_t)stages * stage_bytes;          // EPI_WARPS x 4 KB staging
+  uint8_t* tail = stg_base + EPI_WARPS * 4096;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + stages;          // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);   // [BN]
   float* s_scale = s_bias + BN;                                // [BN]
   float* s_shift = s_scale + BN;                               // [BN]
   float* s_head = s_shift + BN;                                // [32]
-  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_head + 32);   // [128]
+  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_head + 32);   // [EPI_WARPS * 32]
 
   const GemmProblem& pr = P.prob;
   const GemmEpilogue& e = pr.epi;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int img = blockIdx.x / pr.m_tiles;
-  const int m0 = (blockIdx.x - img * pr.m_tiles) * GEMM_BM;
-  const int n0 = blockIdx.y * BN;
-  const bool three = pr.terms == 3;
   const int n_main = P.n_main;
   const bool sep_corr = P.sep_corr != 0;
   const int n_acc = n_main + (sep_corr ? 1 : 0);
+  const int acc_bufs = P.acc_bufs;
+  const int n_tiles = pr.N / BN;
+  const int total_tiles = pr.n_img * pr.m_tiles * n_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full_bar + i, 1);
+      mbar_init(tmem_empty_bar + i, EPI_THREADS);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
     tma_prefetch_desc(&P.b_hi);
@@ -88,113 +102,143 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
     }
   }
   if (warp == 1) tmem_alloc_dyn(tmem_holder, P.tmem_cols);
-  if (warp >= 2) {   // per-tile constants
-    const int i = threadIdx.x - 64;
-    if (i < BN) {
-      s_bias[i] = e.bias ? __ldg(e.bias + n0 + i) : 0.f;
-      int co = n0 + i;
-      if (e.map != MAP_PLAIN) co -= (co / e.cout) * e.cout;
-      s_scale[i] = e.a_scale ? __ldg(e.a_scale + co) : 1.f;
-      s_shift[i] = e.a_scale ? __ldg(e.a_shift + co) : 0.f;
-    }
-    if (i < 32) s_head[i] = e.head_w ? __ldg(e.head_w + i) : 0.f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0;
       bool ok = true;
-      for (int t = 0; t < pr.ntaps && ok; ++t) {
-        const GemmTap tap = pr.taps[t];
-        for (int c = 0; c < tap.nch; c += BK, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
-          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        const int img = mt / pr.m_tiles;
+        const int m0 = (mt - img * pr.m_tiles) * GEMM_BM;
+        const int n0 = nt * BN;
+        for (int t = 0; t < pr.ntaps && ok; ++t) {
+          const GemmTap tap = pr.taps[t];
           const bool a_lo = three || tap.both;
-          mbar_expect_tx(full_bar + s, (a_lo ? 2u : 1u) * A_BYTES + (three ? 2u : 1u) * B_BYTES);
-          tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-          tma_load_2d(st + 2 * A_BYTES, &P.b_hi, full_bar + s, tap.k_off + c, n0);
-          if (a_lo) tma_load_3d(st + A_BYTES, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-          if (three) tma_load_2d(st + 2 * A_BYTES + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
+          const uint32_t tx = (a_lo ? 2u : 1u) * A_BYTES + (three ? 2u : 1u) * B_BYTES;
+          for (int c = 0; c < tap.nch; c += BK, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (it / stages) & 1;
+            if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+            uint8_t* st = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(full_bar + s, tx);
+            tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
+            tma_load_2d(st + off_b, &P.b_hi, full_bar + s, tap.k_off + c, n0);
+            if (a_lo) tma_load_3d(st + A_BYTES, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
+            if (three) tma_load_2d(st + off_b + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
-      int it = 0;
-      uint32_t started = 0;     // bit a: accumulator a has been written
+      int it = 0, ti = 0;
       bool ok = true;
-      for (int t = 0; t < pr.ntaps && ok; ++t) {
-        const int nch = pr.taps[t].nch;
-        const bool both = pr.taps[t].both != 0;
-        for (int c = 0; c < nch; c += BK, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t a_lo = a_hi + A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * A_BYTES;
-          const uint32_t b_lo = b_hi + B_BYTES;
-          const int am = it % n_main;
-          const int ac = sep_corr ? n_main : am;
-          const uint32_t d_main = tmem_base + am * BN;
-          const uint32_t d_corr = tmem_base + ac * BN;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
+        const int ab = ti % acc_bufs;
+        const uint32_t aph = (ti / acc_bufs) & 1;
+        if (!mbar_wait(tmem_empty_bar + ab, aph ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + ab * n_acc * BN;
+        uint32_t started = 0;     // bit a: accumulator a of this tile has been written
+        int ci = 0;               // chunk index inside the tile
+        for (int t = 0; t < pr.ntaps && ok; ++t) {
+          const int nch = pr.taps[t].nch;
+          const bool both = pr.taps[t].both != 0;
+          for (int c = 0; c < nch; c += BK, ++it, ++ci) {
+            const int s = it % stages;
+            const uint32_t ph = (it / stages) & 1;
+            if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + off_b;
+            const uint32_t b_lo = b_hi + B_BYTES;
+            const int am = ci % n_main;
+            const int ac = sep_corr ? n_main : am;
+            const uint32_t d_main = acc0 + am * BN;
+            const uint32_t d_corr = acc0 + ac * BN;
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            const uint64_t da_hi = make_smem_desc(a_hi + k * 32, ROW_BYTES);
-            const uint64_t db_hi = make_smem_desc(b_hi + k * 32, ROW_BYTES);
-            umma_f16(d_main, da_hi, db_hi, idesc, (started >> am) & 1u);
-            started |= 1u << am;
-            if (three) {
-              umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, (started >> ac) & 1u);
-              started |= 1u << ac;
-              umma_f16(d_corr, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
-            } else if (both) {
-              umma_f16(d_main, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
+            for (int k = 0; k < KSTEPS; ++k) {
+              const uint64_t da_hi = make_smem_desc(a_hi + k * 32, ROW_BYTES);
+              const uint64_t db_hi = make_smem_desc(b_hi + k * 32, ROW_BYTES);
+              umma_f16(d_main, da_hi, db_hi, idesc, (started >> am) & 1u);
+              started |= 1u << am;
+              if (three) {
+                umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, (started >> ac) & 1u);
+                started |= 1u << ac;
+                umma_f16(d_corr, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
+              } else if (both) {
+                umma_f16(d_main, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
+              }
             }
+            umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
           }
-          umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
         }
+        umma_commit(tmem_full_bar + ab);  // all accumulators of this tile complete
       }
-      umma_commit(tmem_full_bar);       // all accumulators complete
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int rt = q * 32 + lane;       // row inside the tile
-    const int r = m0 + rt;              // GEMM row inside the image
-    const bool row_ok = r < e.rows_in;
-    if (mbar_wait(tmem_full_bar, 0, e.err, ERR_PIPE_EPILOGUE)) {
+    const int half = ew >> 2;           // with 8 epilogue warps: which column chunks this warp takes
+    constexpr int CHUNK_STEP = EPI_WARPS / 4;
+    float4* stg_f = reinterpret_cast<float4*>(stg_base) + (size_t)ew * 256;            // 4 KB per warp
+    uint4* stg_h = reinterpret_cast<uint4*>(stg_f);                                    // halves alias the same 4 KB
+    uint4* stg_l = stg_h + 128;
+    RowInfo* rows = s_rows + ew * 32;
+    const int et = threadIdx.x - 64;
+    int prev_n0 = -1, ti = 0;
+    bool ovf = false, ok = true;
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
+      const int nt = tile % n_tiles, mt = tile / n_tiles;
+      const int img = mt / pr.m_tiles;
+      const int m0 = (mt - img * pr.m_tiles) * GEMM_BM;
+      const int n0 = nt * BN;
+      if (n0 != prev_n0) {   // per-N-tile constants (uniform branch)
+        epi_bar_sync(EPI_THREADS);
+        if (et < BN) {
+          s_bias[et] = e.bias ? __ldg(e.bias + n0 + et) : 0.f;
+          int co = n0 + et;
+          if (e.map != MAP_PLAIN) co -= (co / e.cout) * e.cout;
+          s_scale[et] = e.a_scale ? __ldg(e.a_scale + co) : 1.f;
+          s_shift[et] = e.a_scale ? __ldg(e.a_shift + co) : 0.f;
+        }
+        if (et < 32) s_head[et] = e.head_w ? __ldg(e.head_w + et) : 0.f;
+        epi_bar_sync(EPI_THREADS);
+        prev_n0 = n0;
+      }
+      const int ab = ti % acc_bufs;
+      const uint32_t aph = (ti / acc_bufs) & 1;
+      if (!mbar_wait(tmem_full_bar + ab, aph, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       tc_fence_after();
-      // staging (aliases pipeline stages 0-1: every MMA that read them has completed)
-      float4* stg_f = reinterpret_cast<float4*>(smem) + (size_t)q * 256;                 // 4 KB per warp
-      uint4* stg_h = reinterpret_cast<uint4*>(smem + 16384) + (size_t)q * 256;           // 2 x 2 KB per warp
-      uint4* stg_l = stg_h + 128;
-      RowInfo* rows = s_rows + q * 32;
+      const uint32_t acc0 = tmem_base + ab * n_acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const int r = m0 + q * 32 + lane;   // GEMM row inside the image
+      const bool row_ok = r < e.rows_in;
       float head_acc = 0.f;
-      bool ovf = false;
       const bool pad_plain = (e.map == MAP_PLAIN) && e.Wp > 0 && (r % e.Wp) == e.Wp - 1;
       int cth = 0, ctw = 0;
       if (e.map == MAP_CONVT2D) { cth = r / e.Wp; ctw = r - cth * e.Wp; }
 
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = half; j < BN / 32; j += CHUNK_STEP) {
         const int nb = n0 + j * 32;
         // ---- accumulators -> registers, summed in fp32 round-to-nearest
         float v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 32, v);
+        tmem_ld_32x32(acc0 + j * 32, v);
         for (int a = 1; a < n_acc; ++a) {
           float w[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + j * 32, w);
+          tmem_ld_32x32(acc0 + a * BN + j * 32, w);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += w[i];
         }
@@ -306,7 +350,7 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
               if (e.act == ACT_LRELU) a = a > 0.f ? a : a * e.slope;
               else if (e.act == ACT_ELU) a = a > 0.f ? a : expm1f(a);
               if (pad) a = 0.f;
-              ovf |= !(fabsf(a) <= 65504.f);
+              ovf |= row_ok && !(fabsf(a) <= 65504.f);
               h[k] = __float2half_rn(a);
               l[k] = __float2half_rn(a - __half2float(h[k]));
             }
@@ -326,9 +370,12 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
           }
         }
       }
-      if (ovf && row_ok && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
-      epilogue_head(e, img, r, head_acc);
+      // this thread is done reading the accumulator buffer: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar + ab);
+      if (half == 0) epilogue_head(e, img, r, head_acc);
     }
+    if (ovf && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
   }
   tc_fence_before();
   __syncthreads();
@@ -338,32 +385,37 @@ __global__ void __launch_bounds__(192, (BN <= 64 ? 3 : 2)) gemm_tc_kernel(const 
   }
 }
 
-template <int BN, int BK>
+// ---------------------------------------------------------------------------------------------- host side
+static int epi_warps_for(int bn) { return bn == 32 ? 4 : 8; }
+
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms) {
+  const size_t stage = (size_t)planes_a * GEMM_BM * bk * 2 + (size_t)(terms == 3 ? 2 : 1) * bn * bk * 2;
+  const int ew = epi_warps_for(bn);
+  return stages * stage + ew * 4096 + (2 * stages + 4) * 8 + 16 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
+}
+
+template <int BN, int BK, int EW>
 static cudaError_t launch_one(const GemmTcParams& p, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = 2 * (GEMM_BM * BK * 2 + BN * BK * 2);
-  const size_t smem = (size_t)p.stages * STAGE_BYTES + (2 * p.stages + 1) * 8 + 16 + (3 * BN + 32) * 4 + 128 * 8 + 1024;
+  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid(p.prob.n_img * p.prob.m_tiles, p.prob.N / BN);
-  gemm_tc_kernel<BN, BK><<<grid, 192, smem, stream>>>(p);
+  gemm_tc_kernel<BN, BK, EW><<<p.grid, 64 + 32 * EW, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-int gemm_tc_stage_bytes(int bn, int bk) { return 2 * (GEMM_BM * bk * 2 + bn * bk * 2); }
-
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream) {
   if (bk == 64) {
-    if (bn == 128) return launch_one<128, 64>(p, stream);
-    if (bn == 64) return launch_one<64, 64>(p, stream);
-    if (bn == 32) return launch_one<32, 64>(p, stream);
+    if (bn == 128) return launch_one<128, 64, 8>(p, stream);
+    if (bn == 64) return launch_one<64, 64, 8>(p, stream);
+    if (bn == 32) return launch_one<32, 64, 4>(p, stream);
   } else if (bk == 32) {
-    if (bn == 128) return launch_one<128, 32>(p, stream);
-    if (bn == 64) return launch_one<64, 32>(p, stream);
-    if (bn == 32) return launch_one<32, 32>(p, stream);
+    if (bn == 128) return launch_one<128, 32, 8>(p, stream);
+    if (bn == 64) return launch_one<64, 32, 8>(p, stream);
+    if (bn == 32) return launch_one<32, 32, 4>(p, stream);
   }
   return cudaErrorInvalidValue;
 }
