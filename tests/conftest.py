@@ -12,6 +12,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the CPU oracle (torch convs) gets slower, not faster, beyond ~16 threads on the many-core GPU hosts
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
 
 
 @pytest.fixture(scope="session")
@@ -19,7 +22,6 @@ def state():
     """Seeded synthetic weights shared by oracle and engine (weights.make_state)."""
     import torch
     from voicefixer_main_b200.weights import make_state
-    torch.set_num_threads(os.cpu_count() or 1)
     return make_state(1234)
 
 

@@ -32,6 +32,7 @@ GEMM_CASES = [
     (2, 500, 128, 128, 3, 27),   # (128, 64), dilated taps, OOB rows
     (3, 40, 384, 384, 9, 2),     # tiny image, 3 N tiles, long K
     (1, 1000, 64, 192, 2, 1),    # N = 192 -> BN 64
+    (2, 700, 128, 512, 3, 3),    # terms = 1 -> BN 256
 ]
 
 

@@ -523,10 +523,12 @@ struct Builder {
     if (bk == 64 && !promoted) {
       int ksum = 0;
       for (auto& t : taps) ksum += t.nch;
-      if (ksum <= 1024) bk = 32;
+      if (ksum <= 256) bk = 32;
     }
     const int N = W.N;
-    const int bn = (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
+    // 1-term (hi-only) GEMMs stream half the operand bytes per MMA, so they are L2-bandwidth bound at 128-wide
+    // tiles: use 256-wide N tiles where the accumulator budget allows (one accumulator, double buffered)
+    const int bn = (terms == 1 && N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
     if (N % 32) { rc = fail(ctx, VF_EINVAL, "GEMM N=%d not a multiple of 32", N); return; }
     int k = 0;
     for (auto& t : taps) {
@@ -590,7 +592,7 @@ struct Builder {
       tp.planes_a = (terms == 3 || any_both) ? 2 : 1;
       auto pow2 = [](int x) { int c = 32; while (c < x) c *= 2; return c; };
       // occupancy: small-K tiles are bound by loads/stores -> several persistent CTAs per SM; large-K -> one
-      const int reg_limit = bn == 32 ? 3 : (bn == 64 ? 2 : 1);
+      const int reg_limit = bn == 32 ? 3 : (bn == 64 ? 2 : 1);   // matches __launch_bounds__ in gemm_tc.cu
       int ctas = (k <= 1024) ? reg_limit : 1;
       int stages = 0;
       for (; ctas >= 1; --ctas) {

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int epi_warps_for(int bn) { return bn == 32 ? 4 : 8; }
+static int epi_warps_for(int bn) { return (bn == 32 || bn == 256) ? 4 : 8; }
 
 size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms) {
   const size_t stage = (size_t)planes_a * GEMM_BM * bk * 2 + (size_t)(terms == 3 ? 2 : 1) * bn * bk * 2;
@@ -409,10 +409,12 @@ static cudaError_t launch_one(const GemmTcParams& p, cudaStream_t stream) {
 
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream) {
   if (bk == 64) {
+    if (bn == 256) return launch_one<256, 64, 4>(p, stream);
     if (bn == 128) return launch_one<128, 64, 8>(p, stream);
     if (bn == 64) return launch_one<64, 64, 8>(p, stream);
     if (bn == 32) return launch_one<32, 64, 4>(p, stream);
   } else if (bk == 32) {
+    if (bn == 256) return launch_one<256, 32, 4>(p, stream);
     if (bn == 128) return launch_one<128, 32, 8>(p, stream);
     if (bn == 64) return launch_one<64, 32, 8>(p, stream);
     if (bn == 32) return launch_one<32, 32, 4>(p, stream);
