@@ -44,7 +44,26 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
 
 }  // namespace
 
-template <int BN, int BK, int EPI_WARPS>
+// Epilogue helpers: 32 fp32 values of one row -> packed half2 hi (and lo) words.
+__device__ __forceinline__ void pack_hi(const float (&v)[32], uint32_t (&hi)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+__device__ __forceinline__ void pack_hi_lo(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+template <int BN, int BK, int EPI_WARPS, bool THREE>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64 ? 2 : 1)))
     gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
   constexpr int A_BYTES = GEMM_BM * BK * 2;
@@ -53,12 +72,12 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   constexpr int KSTEPS = BK / 16;
   constexpr int EPI_THREADS = 32 * EPI_WARPS;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // 1024-byte alignment by offset arithmetic (keeps the pointer in the shared address space: LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stages = P.stages;
-  const bool three = P.prob.terms == 3;
   const int planes_a = P.planes_a;                      // 2 when any tap contracts the lo plane of A
-  const int stage_bytes = planes_a * A_BYTES + (three ? 2 : 1) * B_BYTES;
+  const int stage_bytes = planes_a * A_BYTES + (THREE ? 2 : 1) * B_BYTES;
   const int off_b = planes_a * A_BYTES;
   uint8_t* stg_base = smem + (size_t)stages * stage_bytes;          // EPI_WARPS x 4 KB staging
   uint8_t* tail = stg_base + EPI_WARPS * 4096;
@@ -67,7 +86,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   uint64_t* tmem_full_bar = empty_bar + stages;          // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_holder + 2);   // [BN]
+  float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
   float* s_shift = s_scale + BN;                               // [BN]
   float* s_head = s_shift + BN;                                // [32]
@@ -96,7 +115,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
     tma_prefetch_desc(&P.b_hi);
-    if (three) {
+    if (THREE) {
       tma_prefetch_desc(&P.a_lo[0]);
       tma_prefetch_desc(&P.b_lo);
     }
@@ -119,8 +138,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
         const int n0 = nt * BN;
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const GemmTap tap = pr.taps[t];
-          const bool a_lo = three || tap.both;
-          const uint32_t tx = (a_lo ? 2u : 1u) * A_BYTES + (three ? 2u : 1u) * B_BYTES;
+          const bool a_lo = THREE || tap.both;
+          const uint32_t tx = (a_lo ? 2u : 1u) * A_BYTES + (THREE ? 2u : 1u) * B_BYTES;
           for (int c = 0; c < tap.nch; c += BK, ++it) {
             const int s = it % stages;
             const uint32_t ph = (it / stages) & 1;
@@ -130,7 +149,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
             tma_load_2d(st + off_b, &P.b_hi, full_bar + s, tap.k_off + c, n0);
             if (a_lo) tma_load_3d(st + A_BYTES, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-            if (three) tma_load_2d(st + off_b + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
+            if (THREE) tma_load_2d(st + off_b + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
           }
         }
       }
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
               const uint64_t db_hi = make_smem_desc(b_hi + k * 32, ROW_BYTES);
               umma_f16(d_main, da_hi, db_hi, idesc, (started >> am) & 1u);
               started |= 1u << am;
-              if (three) {
+              if (THREE) {
                 umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, (started >> ac) & 1u);
                 started |= 1u << ac;
                 umma_f16(d_corr, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
@@ -198,8 +217,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     uint4* stg_l = stg_h + 128;
     RowInfo* rows = s_rows + ew * 32;
     const int et = threadIdx.x - 64;
+    // loop-invariant epilogue configuration in registers
+    const int map = e.map, Wp = e.Wp, cout = e.cout, rows_in = e.rows_in;
+    const bool has_affine = e.a_scale != nullptr, has_bias = e.bias != nullptr;
+    const bool want_a = e.out_a.hi != nullptr, want_r = e.out_r.hi != nullptr, want_raw = e.out_raw != nullptr;
+    const bool has_resid = e.resid != nullptr, has_head = e.head_w != nullptr;
+    const int act = e.act;
+    const float slope = e.slope;
+    // lane roles for the row-major global accesses
+    const int f_row = lane >> 3, f_c16 = lane & 7;       // fp32: 4 rows x 128 B per instruction
+    const int h_row = lane >> 2, h_c16 = lane & 3;       // fp16: 8 rows x 64 B per instruction
     int prev_n0 = -1, ti = 0;
-    bool ovf = false, ok = true;
+    float amax = 0.f;
+    bool ok = true;
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
       const int nt = tile % n_tiles, mt = tile / n_tiles;
       const int img = mt / pr.m_tiles;
@@ -207,14 +237,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
       const int n0 = nt * BN;
       if (n0 != prev_n0) {   // per-N-tile constants (uniform branch)
         epi_bar_sync(EPI_THREADS);
-        if (et < BN) {
-          s_bias[et] = e.bias ? __ldg(e.bias + n0 + et) : 0.f;
-          int co = n0 + et;
-          if (e.map != MAP_PLAIN) co -= (co / e.cout) * e.cout;
-          s_scale[et] = e.a_scale ? __ldg(e.a_scale + co) : 1.f;
-          s_shift[et] = e.a_scale ? __ldg(e.a_shift + co) : 0.f;
+        for (int i = et; i < BN; i += EPI_THREADS) {
+          s_bias[i] = has_bias ? __ldg(e.bias + n0 + i) : 0.f;
+          int co = n0 + i;
+          if (map != MAP_PLAIN) co -= (co / cout) * cout;
+          s_scale[i] = has_affine ? __ldg(e.a_scale + co) : 1.f;
+          s_shift[i] = has_affine ? __ldg(e.a_shift + co) : 0.f;
         }
-        if (et < 32) s_head[et] = e.head_w ? __ldg(e.head_w + et) : 0.f;
+        if (et < 32) s_head[et] = has_head ? __ldg(e.head_w + et) : 0.f;
         epi_bar_sync(EPI_THREADS);
         prev_n0 = n0;
       }
@@ -224,11 +254,22 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
       tc_fence_after();
       const uint32_t acc0 = tmem_base + ab * n_acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const int r = m0 + q * 32 + lane;   // GEMM row inside the image
-      const bool row_ok = r < e.rows_in;
+      const bool row_ok = r < rows_in;
       float head_acc = 0.f;
-      const bool pad_plain = (e.map == MAP_PLAIN) && e.Wp > 0 && (r % e.Wp) == e.Wp - 1;
       int cth = 0, ctw = 0;
-      if (e.map == MAP_CONVT2D) { cth = r / e.Wp; ctw = r - cth * e.Wp; }
+      uint32_t orow = 0, flags = 0;
+      if (map == MAP_PLAIN) {             // row mapping independent of the column chunk
+        if (row_ok) {
+          orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + r);
+          flags = kRowValid | ((Wp > 0 && (r % Wp) == Wp - 1) ? kRowPad : 0);
+        }
+        __syncwarp();
+        rows[lane] = RowInfo{orow, flags};
+        __syncwarp();
+      } else if (map == MAP_CONVT2D) {
+        cth = r / Wp;
+        ctw = r - cth * Wp;
+      }
 
 #pragma unroll 1
       for (int j = half; j < BN / 32; j += CHUNK_STEP) {
@@ -242,41 +283,47 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += w[i];
         }
-        // ---- row mapping for this column chunk
-        int co0 = nb, phase = 0;
-        if (e.map != MAP_PLAIN) { phase = nb / e.cout; co0 = nb - phase * e.cout; }
-        uint32_t orow = 0, flags = 0;
-        if (row_ok) {
-          if (e.map == MAP_PLAIN) {
-            orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + r);
-            flags = kRowValid | (pad_plain ? kRowPad : 0);
-          } else if (e.map == MAP_CONVT2D) {
-            const int ph = phase >> 1, pw = phase & 1;
-            orow = (uint32_t)((size_t)img * e.out_img_rows + (size_t)(2 * cth + ph) * (2 * e.Wp) + 2 * ctw + pw);
-            flags = kRowValid | ((ctw == e.Wp - 1 && pw == 1) ? kRowPad : 0);
-          } else {
-            const long t = (long)r * e.ct_stride + phase - e.ct_pad;
-            if (t >= 0 && t < e.out_rows_valid) {
-              orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + t);
-              flags = kRowValid;
+        int co0 = nb;
+        if (map != MAP_PLAIN) {           // transposed convs: the output row depends on the phase of this chunk
+          const int phase = nb / cout;
+          co0 = nb - phase * cout;
+          orow = 0; flags = 0;
+          if (row_ok) {
+            if (map == MAP_CONVT2D) {
+              const int ph = phase >> 1, pw = phase & 1;
+              orow = (uint32_t)((size_t)img * e.out_img_rows + (size_t)(2 * cth + ph) * (2 * Wp) + 2 * ctw + pw);
+              flags = kRowValid | ((ctw == Wp - 1 && pw == 1) ? kRowPad : 0);
+            } else {
+              const long t = (long)r * e.ct_stride + phase - e.ct_pad;
+              if (t >= 0 && t < e.out_rows_valid) {
+                orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + t);
+                flags = kRowValid;
+              }
             }
           }
+          __syncwarp();
+          rows[lane] = RowInfo{orow, flags};
         }
-        __syncwarp();
-        rows[lane] = RowInfo{orow, flags};
         // ---- bias
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += s_bias[j * 32 + i];
-        // ---- residual: coalesced global -> staging -> own row
-        if (e.resid) {
-          const size_t rbase = ((size_t)img * e.rows_in + m0 + q * 32) * e.resid_ld + co0;
+        if (has_bias) {
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + j * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3), c16 = lane & 7;
+            const float4 b4 = bp[i];
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
+        }
+        // ---- residual: coalesced global -> staging -> own row
+        if (has_resid) {
+          const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + f_row;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + q * 32 + rr < e.rows_in)
-              x = __ldg(reinterpret_cast<const float4*>(e.resid + rbase + (size_t)rr * e.resid_ld) + c16);
-            stg_f[sw128(rr, c16)] = x;
+            if (m0 + q * 32 + rr < rows_in)
+              x = __ldg(reinterpret_cast<const float4*>(e.resid + rbase + (size_t)rr * e.resid_ld) + f_c16);
+            stg_f[sw128(rr, f_c16)] = x;
           }
           __syncwarp();
 #pragma unroll
@@ -291,81 +338,90 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
         // ---- fp32 output
-        if (e.out_raw) {
+        if (want_raw) {
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) stg_f[sw128(lane, i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3), c16 = lane & 7;
+            const int rr = 4 * i + f_row;
             const RowInfo ri = rows[rr];
             if (ri.flags & kRowValid)
-              reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[c16] = stg_f[sw128(rr, c16)];
+              reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[sw128(rr, f_c16)];
           }
         }
         // ---- raw hi/lo planes
-        if (e.out_r.hi) {
+        if (want_r) {
+          uint32_t hi[16], lo[16];
+          pack_hi_lo(v, hi, lo);
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __align__(16) __half h[8];
-            __align__(16) __half l[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              h[k] = __float2half_rn(v[8 * i + k]);
-              l[k] = __float2half_rn(v[8 * i + k] - __half2float(h[k]));
-            }
-            stg_h[sw64(lane, i)] = *reinterpret_cast<const uint4*>(h);
-            stg_l[sw64(lane, i)] = *reinterpret_cast<const uint4*>(l);
+            stg_h[sw64(lane, i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            stg_l[sw64(lane, i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + (lane >> 2), c16 = lane & 3;
+            const int rr = 8 * i + h_row;
             const RowInfo ri = rows[rr];
             if (ri.flags & kRowValid) {
               const size_t o = (size_t)ri.orow * e.out_r.ld + e.out_r.c_off + co0;
-              reinterpret_cast<uint4*>(e.out_r.hi + o)[c16] = stg_h[sw64(rr, c16)];
-              reinterpret_cast<uint4*>(e.out_r.lo + o)[c16] = stg_l[sw64(rr, c16)];
+              reinterpret_cast<uint4*>(e.out_r.hi + o)[h_c16] = stg_h[sw64(rr, h_c16)];
+              reinterpret_cast<uint4*>(e.out_r.lo + o)[h_c16] = stg_l[sw64(rr, h_c16)];
             }
           }
         }
         // ---- fused 1x1 head (N == 32)
-        if (e.head_w) {
+        if (has_head) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) head_acc = fmaf(v[i], s_head[i], head_acc);
         }
         // ---- activated hi/lo planes (consumer's BN affine + activation)
-        if (e.out_a.hi) {
+        if (want_a) {
+          if (has_affine) {
+            const float4* sc = reinterpret_cast<const float4*>(s_scale + j * 32);
+            const float4* sh = reinterpret_cast<const float4*>(s_shift + j * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a4 = sc[i], b4 = sh[i];
+              v[4 * i] = fmaf(v[4 * i], a4.x, b4.x); v[4 * i + 1] = fmaf(v[4 * i + 1], a4.y, b4.y);
+              v[4 * i + 2] = fmaf(v[4 * i + 2], a4.z, b4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], a4.w, b4.w);
+            }
+          }
+          if (act == ACT_LRELU) {           // slope in [0, 1]: max(a, slope * a)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], v[i] * slope);
+          } else if (act == ACT_ELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+          }
+          if (pad) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
+          }
+          uint32_t hi[16], lo[16];
+          if (THREE) pack_hi_lo(v, hi, lo); else pack_hi(v, hi);
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __align__(16) __half h[8];
-            __align__(16) __half l[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int cidx = j * 32 + 8 * i + k;
-              float a = fmaf(v[8 * i + k], s_scale[cidx], s_shift[cidx]);
-              if (e.act == ACT_LRELU) a = a > 0.f ? a : a * e.slope;
-              else if (e.act == ACT_ELU) a = a > 0.f ? a : expm1f(a);
-              if (pad) a = 0.f;
-              ovf |= row_ok && !(fabsf(a) <= 65504.f);
-              h[k] = __float2half_rn(a);
-              l[k] = __float2half_rn(a - __half2float(h[k]));
-            }
-            stg_h[sw64(lane, i)] = *reinterpret_cast<const uint4*>(h);
-            stg_l[sw64(lane, i)] = *reinterpret_cast<const uint4*>(l);
+            stg_h[sw64(lane, i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            if (THREE) stg_l[sw64(lane, i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + (lane >> 2), c16 = lane & 3;
+            const int rr = 8 * i + h_row;
             const RowInfo ri = rows[rr];
             if (ri.flags & kRowValid) {
               const size_t o = (size_t)ri.orow * e.out_a.ld + e.out_a.c_off + co0;
-              reinterpret_cast<uint4*>(e.out_a.hi + o)[c16] = stg_h[sw64(rr, c16)];
-              if (three) reinterpret_cast<uint4*>(e.out_a.lo + o)[c16] = stg_l[sw64(rr, c16)];
+              reinterpret_cast<uint4*>(e.out_a.hi + o)[h_c16] = stg_h[sw64(rr, h_c16)];
+              if (THREE) reinterpret_cast<uint4*>(e.out_a.lo + o)[h_c16] = stg_l[sw64(rr, h_c16)];
             }
           }
         }
@@ -375,7 +431,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
       mbar_arrive(tmem_empty_bar + ab);
       if (half == 0) epilogue_head(e, img, r, head_acc);
     }
-    if (ovf && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
+    // NaN compares false against everything: !(amax <= 65504) also catches it when it reaches amax via fabsf/fmaxf of inf
+    if (!(amax <= 65504.f) && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
   }
   tc_fence_before();
   __syncthreads();
@@ -386,35 +443,39 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int epi_warps_for(int bn) { return (bn == 32 || bn == 256) ? 4 : 8; }
+static int epi_warps_for(int bn) { return bn == 32 ? 4 : 8; }
 
 size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms) {
   const size_t stage = (size_t)planes_a * GEMM_BM * bk * 2 + (size_t)(terms == 3 ? 2 : 1) * bn * bk * 2;
   const int ew = epi_warps_for(bn);
-  return stages * stage + ew * 4096 + (2 * stages + 4) * 8 + 16 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
+  return stages * stage + ew * 4096 + (2 * stages + 4) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
 }
 
-template <int BN, int BK, int EW>
-static cudaError_t launch_one(const GemmTcParams& p, cudaStream_t stream) {
+template <int BN, int BK, int EW, bool THREE>
+static cudaError_t launch_cfg(const GemmTcParams& p, cudaStream_t stream) {
   const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW, THREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<BN, BK, EW><<<p.grid, 64 + 32 * EW, smem, stream>>>(p);
+  gemm_tc_kernel<BN, BK, EW, THREE><<<p.grid, 64 + 32 * EW, smem, stream>>>(p);
   return cudaGetLastError();
+}
+template <int BN, int BK, int EW>
+static cudaError_t launch_one(const GemmTcParams& p, cudaStream_t stream) {
+  return p.prob.terms == 3 ? launch_cfg<BN, BK, EW, true>(p, stream) : launch_cfg<BN, BK, EW, false>(p, stream);
 }
 
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream) {
   if (bk == 64) {
-    if (bn == 256) return launch_one<256, 64, 4>(p, stream);
+    if (bn == 256) return p.prob.terms == 1 ? launch_cfg<256, 64, 8, false>(p, stream) : cudaErrorInvalidValue;
     if (bn == 128) return launch_one<128, 64, 8>(p, stream);
     if (bn == 64) return launch_one<64, 64, 8>(p, stream);
     if (bn == 32) return launch_one<32, 64, 4>(p, stream);
   } else if (bk == 32) {
-    if (bn == 256) return launch_one<256, 32, 4>(p, stream);
+    if (bn == 256) return p.prob.terms == 1 ? launch_cfg<256, 32, 8, false>(p, stream) : cudaErrorInvalidValue;
     if (bn == 128) return launch_one<128, 32, 8>(p, stream);
     if (bn == 64) return launch_one<64, 32, 8>(p, stream);
     if (bn == 32) return launch_one<32, 32, 4>(p, stream);
