@@ -281,7 +281,7 @@ def to_int16(frames: np.ndarray) -> np.ndarray:
 
 
 def restore(sd, wav: torch.Tensor, cfg: Optional[VocoderConfig] = None, exact_stft: bool = False,
-            seg_samples: int = SEG_SAMPLES, stages: Optional[dict] = None) -> torch.Tensor:
+            seg_samples: int = SEG_SAMPLES, stages: Optional[dict] = None, unify_energy: bool = False) -> torch.Tensor:
     """handler() of eval_gsr_voicefixer.py:37-77 for a batch of equal-length clips
     wav [B,N] -> [B,N]: independent 60 s segments, stages A->B->C, peak normalise, trim, concat."""
     cfg = cfg or VocoderConfig()
@@ -293,6 +293,8 @@ def restore(sd, wav: torch.Tensor, cfg: Optional[VocoderConfig] = None, exact_st
         _, mel_noisy = pre(seg[:, None, :], exact=exact_stft)
         log_mel = generator_forward(sd, mel_noisy.float())
         denoised = from_log(log_mel)
+        if unify_energy:                                          # eval_gsr_voicefixer.py:54-55
+            denoised, _ = amp_to_original_f(mel_est=denoised, mel_target=mel_noisy.float())
         out = vocoder_forward(sd, denoised, cfg)
         out = peak_normalize(out)
         out = trim_center(out, seg.shape[-1])

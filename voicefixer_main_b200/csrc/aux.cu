@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) voc_condition_kernel(VocCondParams p) {
     for (int i = 0; i < 8; ++i) {
       float m = __ldg(src + i);
       if (p.is_log) m = exp10f(fminf(m, 5.f));                            // from_log, pytorch_util.py:161-163
+      if (p.band_sums) m *= __ldg(p.band_sums + 2 * b) / __ldg(p.band_sums + 2 * b + 1);
       const float v = fabsf(m) / __ldg(p.weight + g * 8 + i);
       const float s = 20.f * log10f(fmaxf(v, p.amp_floor)) - p.ref_db;
       c[i] = fminf(fmaxf((s - p.min_db) / (-p.min_db), 0.f), 1.f);
@@ -156,6 +157,31 @@ __global__ void __launch_bounds__(256) voc_condition_kernel(VocCondParams p) {
   }
   split_store8(p.out.hi, p.out.lo, ((size_t)b * p.Tv + tv) * 128 + g * 8, c);
 }
+__global__ void __launch_bounds__(256) band_energy_kernel(const float* tgt, const float* logest, int T, float* sums) {
+  const int b = blockIdx.y;
+  float st = 0.f, se = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T * 20; i += gridDim.x * blockDim.x) {
+    const size_t idx = ((size_t)b * T + i / 20) * 128 + 5 + i % 20;
+    st += __ldg(tgt + idx);
+    se += exp10f(fminf(__ldg(logest + idx), 5.f));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    st += __shfl_xor_sync(0xffffffffu, st, o);
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sums + 2 * b, st);
+    atomicAdd(sums + 2 * b + 1, se);
+  }
+}
+cudaError_t launch_band_energy(const float* mel_target_lin, const float* logmel_est, int batch, int T, float* sums,
+                               cudaStream_t stream) {
+  dim3 grid(8, batch);
+  band_energy_kernel<<<grid, 256, 0, stream>>>(mel_target_lin, logmel_est, T, sums);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_voc_condition(const VocCondParams& p, cudaStream_t stream) {
   const size_t total = (size_t)p.batch * p.Tv * 16;
   voc_condition_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);

@@ -101,6 +101,7 @@ struct Plan {
   float* d_logmel_in = nullptr;  // [B, T, 128] log10 mel (UNet input)
   float* d_logmel_out = nullptr; // [B, T, 128]
   float* d_voc_wav = nullptr;    // [B, L]
+  float* d_band = nullptr;       // [B][2] low-band energy sums (unify_energy)
   unsigned int* d_peak = nullptr;
   long L = 0;
   // op slots patched per call
@@ -119,7 +120,7 @@ struct vf_ctx {
   bool loaded = false;
   EncodeTiledFn encode = nullptr;
   int sm_count = 148;
-  int unet_terms = 3, voc_terms = 1, validate_simt = 0;
+  int unet_terms = 3, voc_terms = 1, validate_simt = 0, unify_energy = 0;
   int64_t launches = 0;
   int* d_err = nullptr;      // [0] device error code, [1] negative-input count
   // tables
@@ -959,6 +960,7 @@ int get_plan(vf_ctx* ctx, int batch, int frames, Plan** out) {
   plan->d_mel = b.alloc<float>(mel_n);
   plan->d_logmel_in = b.alloc<float>(mel_n);
   plan->d_logmel_out = b.alloc<float>(mel_n);
+  plan->d_band = b.alloc<float>(2 * (size_t)batch);
   int rc = b.rc;
   if (!rc) rc = build_unet(ctx, b, plan.get());
   if (!rc) rc = build_vocoder(ctx, b, plan.get());
@@ -1176,6 +1178,7 @@ VF_API int vf_vocoder(vf_ctx* ctx, const float* mel_lin, int batch, int frames, 
   Op& cop = plan->vocoder[plan->cond_op];
   cop.cond.mel = mel_lin;
   cop.cond.is_log = 0;
+  cop.cond.band_sums = nullptr;
   rc = run_ops(ctx, plan->vocoder, st);
   cop.cond.mel = plan->d_logmel_out;
   cop.cond.is_log = 1;
@@ -1206,6 +1209,16 @@ VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float
   rc = run_ops(ctx, plan->unet, st);
   if (rc) return rc;
   if (tm) CK(cudaEventRecord(ctx->ev[2], st));
+  {   // eval_gsr_voicefixer.py:54-55: amp_to_original_f when meta["unify_energy"]
+    Op& cop = plan->vocoder[plan->cond_op];
+    cop.cond.band_sums = nullptr;
+    if (ctx->unify_energy) {
+      CK(cudaMemsetAsync(plan->d_band, 0, 2 * (size_t)batch * sizeof(float), st));
+      CK(launch_band_energy(plan->d_mel, plan->d_logmel_out, batch, frames, plan->d_band, st));
+      ctx->launches++;
+      cop.cond.band_sums = plan->d_band;
+    }
+  }
   rc = run_ops(ctx, plan->vocoder, st);
   if (rc) return rc;
   if (tm) CK(cudaEventRecord(ctx->ev[3], st));
@@ -1298,6 +1311,9 @@ VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value) {
   if (k == "unet_terms" || k == "vocoder_terms") {
     if (value != 1 && value != 3) return fail(ctx, VF_EINVAL, "%s must be 1 or 3", key);
     slot = k == "unet_terms" ? &ctx->unet_terms : &ctx->voc_terms;
+  } else if (k == "unify_energy") {
+    ctx->unify_energy = value ? 1 : 0;     // per-call behaviour, no plan rebuild needed
+    return VF_OK;
   } else if (k == "validate_simt") {
     slot = &ctx->validate_simt;
     value = value ? 1 : 0;

@@ -73,9 +73,16 @@ struct VocCondParams {
   int batch, T, Tv;
   const float* weight;       // [128] per-bin mel weight (divided out)
   float amp_floor, ref_db, min_db, tail_value;
+  const float* band_sums;    // [batch][2] (target, estimate) low-band sums from launch_band_energy, or null:
+                             // amp_to_original_f (tools/utils.py:50-55) scales the estimate by target/estimate
   PlanePtr out;          // [batch, Tv, 128]
 };
 cudaError_t launch_voc_condition(const VocCondParams& p, cudaStream_t stream);
+
+// amp_to_original_f, reduction half: per clip, sums over frames and mel bins [5, int(128*0.2)) of the noisy
+// linear mel (target) and of from_log(restored log-mel) (estimate).  sums must be zeroed before the launch.
+cudaError_t launch_band_energy(const float* mel_target_lin, const float* logmel_est, int batch, int T, float* sums,
+                               cudaStream_t stream);
 
 // nn.ReflectionPad1d(3): rows [3, L+3) of each image are already written; fill 3 + 3 mirrored rows.
 cudaError_t launch_reflect_fill(PlanePtr planes, int batch, int L, int C, int pad, cudaStream_t stream);

@@ -48,7 +48,7 @@ def refresh_model(ckpt):
     model.eval()
 
 
-def restore_array(mdl: VoiceFixer, wav_10k: np.ndarray, device) -> torch.Tensor:
+def restore_array(mdl: VoiceFixer, wav_10k: np.ndarray, device, unify_energy: bool = False) -> torch.Tensor:
     """The segment loop of handler() for one in-memory file: returns [1, N] on `device`."""
     res = []
     break_point = SEG_LENGTH
@@ -56,7 +56,7 @@ def restore_array(mdl: VoiceFixer, wav_10k: np.ndarray, device) -> torch.Tensor:
     while break_point < n + SEG_LENGTH:
         segment = wav_10k[break_point - SEG_LENGTH:break_point]
         seg = torch.from_numpy(np.ascontiguousarray(segment))[None, :].to(device)
-        res.append(mdl.restore(seg))
+        res.append(mdl.restore(seg, unify_energy=unify_energy))
         break_point += SEG_LENGTH
     return torch.cat(res, -1)
 
@@ -68,6 +68,6 @@ def handler(input, output, target, ckpt, device, needrefresh=False, meta={}):
     model = model.to(device)
     metrics = {}
     wav_10k = load_wav(input, sample_rate=44100)
-    out = restore_array(model, wav_10k, model.device)
+    out = restore_array(model, wav_10k, model.device, unify_energy=bool(meta.get("unify_energy", False)))
     save_wave(out[0].detach().cpu().numpy(), fname=output, sample_rate=44100)
     return metrics

@@ -480,9 +480,12 @@ class VoiceFixer:
         return self.forward(mel_orig)
 
     # ---- batched fused path
-    def restore(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """wav [B,N] fp32 on device -> restored [B,N]; one 60 s-or-shorter segment per row."""
-        return self._engine().restore(wav, out)
+    def restore(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None, unify_energy: bool = False) -> torch.Tensor:
+        """wav [B,N] fp32 on device -> restored [B,N]; one 60 s-or-shorter segment per row.
+        unify_energy: apply amp_to_original_f (tools/utils.py:50-55) as handler() does for the SSR test sets."""
+        eng = self._engine()
+        eng.set_option("unify_energy", int(unify_energy))
+        return eng.restore(wav, out)
 
     def restore_host(self, wav_host: torch.Tensor, out_host: torch.Tensor):
         self._engine().restore_host(wav_host, out_host)
