@@ -298,6 +298,9 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+    import torch.distributed as tdist
+    if tdist.is_available() and tdist.is_initialized():
+        tdist.destroy_process_group()
 
 
 if __name__ == "__main__":

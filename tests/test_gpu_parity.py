@@ -216,6 +216,26 @@ def test_unify_energy_matches_amp_to_original_f(model, state):
     assert float((back - plain).pow(2).mean().sqrt()) < 0.25 * delta
 
 
+def test_long_form_segment_loop(model, state, monkeypatch):
+    """BASELINE config 5 path: handler()'s independent-segment loop (eval_gsr_voicefixer.py:47-75), checked
+    against the oracle with a short segment length (ragged tail), then one real 60 s segment for size."""
+    from voicefixer_main_b200 import handler as H
+    wav = O.synth_clips(1, 4 * 44100 + 777, seed=31)[0]
+    monkeypatch.setattr(H, "SEG_LENGTH", 66150)
+    out = H.restore_array(model, wav.numpy(), model.device).cpu()
+    with torch.no_grad():
+        ref = O.restore(state, wav[None], exact_stft=True, seg_samples=66150)
+    assert out.shape == ref.shape == (1, wav.numel())
+    assert float((out - ref).pow(2).mean().sqrt()) < WAV_RMS_TOL
+    monkeypatch.setattr(H, "SEG_LENGTH", 44100 * 60)
+    long = O.synth_clips(1, 44100 * 61, seed=32)[0]
+    out = H.restore_array(model, long.numpy(), model.device)
+    model._engine().check_errors()
+    assert out.shape == (1, 44100 * 61) and bool(torch.isfinite(out).all())
+    tail = model.restore(long[None, 44100 * 60:].cuda())
+    assert torch.equal(out[:, 44100 * 60:], tail)      # segments are independent: the tail is its own restore
+
+
 def test_host_entry_point_and_launch_count(model):
     wav = O.synth_clips(2, 8820, seed=8)
     pin_in, pin_out = wav.pin_memory(), torch.empty_like(wav).pin_memory()

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -578,16 +579,9 @@ struct Builder {
       }
       if (!rc) rc = make_map2(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
       if (!rc) rc = make_map2(&tp.b_lo, W.lo, W.K, N, bk, bn, bk == 64);
-      // accumulation chains (see gemm_tc.cu): keep truncating adds per accumulator <= ~64-72
-      const int ksteps = k / 16;
-      if (terms == 3 && ksteps * 3 > 64) {
-        tp.sep_corr = 1;
-        tp.n_main = ksteps > 96 ? 3 : 1;
-      } else {
-        tp.sep_corr = 0;
-        tp.n_main = 1;
-      }
-      const int n_acc = tp.n_main + tp.sep_corr;
+      // accumulation segments (see gemm_tc.cu): 16 truncating MMAs per chain, then promotion to registers
+      tp.tile_chunks = k / bk;
+      tp.seg_chunks = std::max(1, 16 / (bk / 16));
       bool any_both = false;
       for (auto& t : taps) any_both |= t.both != 0;
       tp.planes_a = (terms == 3 || any_both) ? 2 : 1;
@@ -595,17 +589,17 @@ struct Builder {
       // occupancy: small-K tiles are bound by loads/stores -> several persistent CTAs per SM; large-K -> one
       const int reg_limit = bn == 32 ? 3 : (bn == 64 ? 2 : 1);   // matches __launch_bounds__ in gemm_tc.cu
       int ctas = (k <= 1024) ? reg_limit : 1;
+      if (const char* ov = getenv("VF_TUNE_SMALLK_CTAS")) { if (k <= 1024) ctas = std::max(1, std::min(reg_limit, atoi(ov))); }
       int stages = 0;
       for (; ctas >= 1; --ctas) {
-        tp.acc_bufs = (pow2(2 * n_acc * bn) * ctas <= 512) ? 2 : 1;
-        tp.tmem_cols = pow2(tp.acc_bufs * n_acc * bn);
+        tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
         if (tp.tmem_cols * ctas > 512) continue;
         const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
         for (stages = 8; stages >= 2; --stages)
           if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms) <= per_cta) break;
         if (stages >= 2) break;
       }
-      if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d n_acc=%d)", bn, bk, n_acc); return; }
+      if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }
       tp.stages = stages;
       const long total_tiles = (long)n_img * pr.m_tiles * (N / bn);
       tp.grid = (int)std::min<long>(total_tiles, (long)ctx->sm_count * ctas);

@@ -92,10 +92,9 @@ struct GemmTcParams {
   CUtensorMap a_hi[2], a_lo[2];   // [C, rows, n_img] fp16
   CUtensorMap b_hi, b_lo;         // [Ktot, N] fp16 (K-major)
   int stages;
-  int n_main;      // K loop dealt round-robin over this many TMEM accumulators (truncating adder: short chains)
-  int sep_corr;    // hi*lo + lo*hi accumulate in their own accumulator
-  int tmem_cols;   // power of two >= acc_bufs * (n_main + sep_corr) * BN
-  int acc_bufs;    // 2: accumulator set double buffered in TMEM (epilogue of tile i overlaps MMAs of tile i+1)
+  int tile_chunks; // BK-wide K chunks per output tile
+  int seg_chunks;  // 3-term mode: chunks per accumulation segment (promotion to registers in between)
+  int tmem_cols;   // power of two >= 2 * BN (main ping-pong) [+ 2 * BN correction accumulators in 3-term mode]
   int planes_a;    // smem slots per stage for A: 2 when any tap contracts the lo plane
   int grid;        // persistent CTAs
   GemmProblem prob;

@@ -5,16 +5,17 @@
 //   warp 0     : TMA producer - streams A (activation rows, shifted per tap) and B (packed weights) tiles into a
 //                `stages`-deep shared-memory ring that runs ahead across tile boundaries
 //                (SWIZZLE_128B rows for BK = 64, SWIZZLE_64B for BK = 32)
-//   warp 1     : TMEM owner + single-thread tcgen05.mma issuer; the accumulator set is double buffered in TMEM
-//                when it fits, so tile i+1 accumulates while tile i drains
+//   warp 1     : TMEM owner + single-thread tcgen05.mma issuer; two main accumulators ping-pong in TMEM
 //   warps 2..  : epilogue (4 or 8 warps; one TMEM lane = output row per thread, two warps share a lane quarter
 //                and split the column chunks)
 //
 // Accumulation precision.  The tensor core adds into its fp32 accumulator with truncation, so one long chain
-// of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with one accumulator).
-// The K loop is therefore dealt round-robin over `n_main` independent TMEM accumulators and the two small
-// correction products (hi*lo, lo*hi) go to their own accumulator; the epilogue sums them in fp32
-// round-to-nearest.  This costs TMEM columns, not tensor throughput.
+// of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with one accumulator per
+// tile).  In 3-term mode the K loop is therefore cut into segments of 16 MMAs that ping-pong between two TMEM
+// accumulators; the epilogue warps add each finished segment into registers in fp32 round-to-nearest
+// ("promotion") while the tensor core already works on the next one, and the two small correction products
+// (hi*lo, lo*hi) accumulate in a third, per-tile accumulator.  The same ping-pong is the tile double buffering
+// of the 1-term mode (one segment per tile): tile i+1 accumulates while tile i drains.
 //
 // Epilogue I/O.  A thread owns a row, but global stores are issued row-major by the whole warp: values are
 // transposed through a swizzled shared-memory staging tile so every LDG/STG instruction touches whole
@@ -71,6 +72,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   constexpr int ROW_BYTES = BK * 2;
   constexpr int KSTEPS = BK / 16;
   constexpr int EPI_THREADS = 32 * EPI_WARPS;
+  constexpr int CHUNK_STEP = EPI_WARPS / 4;             // column chunks are dealt to the warps of a lane quarter
+  constexpr int NJ = (BN / 32 + CHUNK_STEP - 1) / CHUNK_STEP;   // chunks per epilogue warp
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // 1024-byte alignment by offset arithmetic (keeps the pointer in the shared address space: LDS/STS, not generic)
@@ -83,9 +86,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   uint8_t* tail = stg_base + EPI_WARPS * 4096;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;          // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* seg_full_bar = empty_bar + stages;           // [2] main accumulator buffer holds a finished segment
+  uint64_t* seg_empty_bar = seg_full_bar + 2;            // [2] ... has been drained by every epilogue thread
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(seg_empty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
   float* s_shift = s_scale + BN;                               // [BN]
@@ -96,12 +99,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   const GemmEpilogue& e = pr.epi;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_main = P.n_main;
-  const bool sep_corr = P.sep_corr != 0;
-  const int n_acc = n_main + (sep_corr ? 1 : 0);
-  const int acc_bufs = P.acc_bufs;
   const int n_tiles = pr.N / BN;
   const int total_tiles = pr.n_img * pr.m_tiles * n_tiles;
+  const int tile_chunks = P.tile_chunks;                 // K chunks per tile
+  const int seg_chunks = THREE ? P.seg_chunks : tile_chunks;   // K chunks per accumulation segment
+  // TMEM columns: main ping-pong M0 [0,BN) M1 [BN,2BN); THREE: correction accumulators C0 [2BN,3BN) C1 [3BN,4BN)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -109,8 +111,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
       mbar_init(empty_bar + s, 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(tmem_full_bar + i, 1);
-      mbar_init(tmem_empty_bar + i, EPI_THREADS);
+      mbar_init(seg_full_bar + i, 1);
+      mbar_init(seg_empty_bar + i, EPI_THREADS);
     }
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
@@ -159,20 +161,23 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
-      int it = 0, ti = 0;
+      int it = 0, ti = 0, g = 0;      // smem chunk counter, tile counter, accumulation-segment counter
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
-        const int ab = ti % acc_bufs;
-        const uint32_t aph = (ti / acc_bufs) & 1;
-        if (!mbar_wait(tmem_empty_bar + ab, aph ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + ab * n_acc * BN;
-        uint32_t started = 0;     // bit a: accumulator a of this tile has been written
-        int ci = 0;               // chunk index inside the tile
+        const uint32_t d_corr = tmem_base + (2 + (ti & 1)) * BN;
+        uint32_t d_main = 0, m_started = 0, c_started = 0;
+        int ci = 0, buf = 0;
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const int nch = pr.taps[t].nch;
           const bool both = pr.taps[t].both != 0;
-          for (int c = 0; c < nch; c += BK, ++it, ++ci) {
+          for (int c = 0; c < nch; c += BK, ++it) {
+            if (ci % seg_chunks == 0) {          // open a segment: its accumulator buffer must have been drained
+              buf = g & 1;
+              if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+              tc_fence_after();
+              d_main = tmem_base + buf * BN;
+              m_started = 0;
+            }
             const int s = it % stages;
             const uint32_t ph = (it / stages) & 1;
             if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
@@ -181,28 +186,28 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             const uint32_t a_lo = a_hi + A_BYTES;
             const uint32_t b_hi = a_hi + off_b;
             const uint32_t b_lo = b_hi + B_BYTES;
-            const int am = ci % n_main;
-            const int ac = sep_corr ? n_main : am;
-            const uint32_t d_main = acc0 + am * BN;
-            const uint32_t d_corr = acc0 + ac * BN;
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k) {
               const uint64_t da_hi = make_smem_desc(a_hi + k * 32, ROW_BYTES);
               const uint64_t db_hi = make_smem_desc(b_hi + k * 32, ROW_BYTES);
-              umma_f16(d_main, da_hi, db_hi, idesc, (started >> am) & 1u);
-              started |= 1u << am;
+              umma_f16(d_main, da_hi, db_hi, idesc, m_started);
+              m_started = 1;
               if (THREE) {
-                umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, (started >> ac) & 1u);
-                started |= 1u << ac;
+                umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, c_started);
+                c_started = 1;
                 umma_f16(d_corr, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
               } else if (both) {
                 umma_f16(d_main, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
               }
             }
             umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
+            ++ci;
+            if (ci % seg_chunks == 0 || ci == tile_chunks) {   // close the segment
+              umma_commit(seg_full_bar + buf);
+              ++g;
+            }
           }
         }
-        umma_commit(tmem_full_bar + ab);  // all accumulators of this tile complete
       }
     }
     __syncwarp();
@@ -211,12 +216,12 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     const int ew = warp - 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = ew >> 2;           // with 8 epilogue warps: which column chunks this warp takes
-    constexpr int CHUNK_STEP = EPI_WARPS / 4;
     float4* stg_f = reinterpret_cast<float4*>(stg_base) + (size_t)ew * 256;            // 4 KB per warp
     uint4* stg_h = reinterpret_cast<uint4*>(stg_f);                                    // halves alias the same 4 KB
     uint4* stg_l = stg_h + 128;
     RowInfo* rows = s_rows + ew * 32;
     const int et = threadIdx.x - 64;
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
     // loop-invariant epilogue configuration in registers
     const int map = e.map, Wp = e.Wp, cout = e.cout, rows_in = e.rows_in;
     const bool has_affine = e.a_scale != nullptr, has_bias = e.bias != nullptr;
@@ -227,7 +232,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     // lane roles for the row-major global accesses
     const int f_row = lane >> 3, f_c16 = lane & 7;       // fp32: 4 rows x 128 B per instruction
     const int h_row = lane >> 2, h_c16 = lane & 3;       // fp16: 8 rows x 64 B per instruction
-    int prev_n0 = -1, ti = 0;
+    const int nseg = (tile_chunks + seg_chunks - 1) / seg_chunks;
+    int prev_n0 = -1, ti = 0, g = 0;
     float amax = 0.f;
     bool ok = true;
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
@@ -248,11 +254,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
         epi_bar_sync(EPI_THREADS);
         prev_n0 = n0;
       }
-      const int ab = ti % acc_bufs;
-      const uint32_t aph = (ti / acc_bufs) & 1;
-      if (!mbar_wait(tmem_full_bar + ab, aph, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
-      tc_fence_after();
-      const uint32_t acc0 = tmem_base + ab * n_acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       const int r = m0 + q * 32 + lane;   // GEMM row inside the image
       const bool row_ok = r < rows_in;
       float head_acc = 0.f;
@@ -271,18 +272,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
         ctw = r - cth * Wp;
       }
 
-#pragma unroll 1
-      for (int j = half; j < BN / 32; j += CHUNK_STEP) {
+      // One 32-column chunk of this thread's row: bias, residual, outputs (see gemm.cuh for the semantics).
+      auto process_chunk = [&](const int j, float (&v)[32]) {
         const int nb = n0 + j * 32;
-        // ---- accumulators -> registers, summed in fp32 round-to-nearest
-        float v[32];
-        tmem_ld_32x32(acc0 + j * 32, v);
-        for (int a = 1; a < n_acc; ++a) {
-          float w[32];
-          tmem_ld_32x32(acc0 + a * BN + j * 32, w);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += w[i];
-        }
         int co0 = nb;
         if (map != MAP_PLAIN) {           // transposed convs: the output row depends on the phase of this chunk
           const int phase = nb / cout;
@@ -304,7 +296,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
           __syncwarp();
           rows[lane] = RowInfo{orow, flags};
         }
-        // ---- bias
         if (has_bias) {
           const float4* bp = reinterpret_cast<const float4*>(s_bias + j * 32);
 #pragma unroll
@@ -313,8 +304,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
           }
         }
-        // ---- residual: coalesced global -> staging -> own row
-        if (has_resid) {
+        if (has_resid) {                  // coalesced global -> staging -> own row
           const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
           __syncwarp();
 #pragma unroll
@@ -337,8 +327,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        // ---- fp32 output
-        if (want_raw) {
+        if (want_raw) {                   // fp32 output
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) stg_f[sw128(lane, i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -351,8 +340,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
               reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[sw128(rr, f_c16)];
           }
         }
-        // ---- raw hi/lo planes
-        if (want_r) {
+        if (want_r) {                     // raw hi/lo planes
           uint32_t hi[16], lo[16];
           pack_hi_lo(v, hi, lo);
           __syncwarp();
@@ -373,13 +361,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             }
           }
         }
-        // ---- fused 1x1 head (N == 32)
-        if (has_head) {
+        if (has_head) {                   // fused 1x1 head (N == 32)
 #pragma unroll
           for (int i = 0; i < 32; ++i) head_acc = fmaf(v[i], s_head[i], head_acc);
         }
-        // ---- activated hi/lo planes (consumer's BN affine + activation)
-        if (want_a) {
+        if (want_a) {                     // activated planes (consumer's BN affine + activation)
           if (has_affine) {
             const float4* sc = reinterpret_cast<const float4*>(s_scale + j * 32);
             const float4* sh = reinterpret_cast<const float4*>(s_shift + j * 32);
@@ -425,13 +411,70 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             }
           }
         }
+      };
+
+      if (THREE) {
+        // Promotion: every finished K segment is added into registers in fp32 round-to-nearest, so no chain of
+        // truncating tensor-core adds is longer than one segment; the small hi*lo + lo*hi sums join at the end.
+        float acc[NJ][32];
+        for (int sg = 0; sg < nseg && ok; ++sg, ++g) {
+          const int buf = g & 1;
+          if (!mbar_wait(seg_full_bar + buf, (g >> 1) & 1, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+          tc_fence_after();
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) {
+            const int j = half + jj * CHUNK_STEP;
+            if (j < BN / 32) {
+              float w[32];
+              tmem_ld_32x32(tmem_base + lane_bits + buf * BN + j * 32, w);
+              if (sg == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[jj][i] = w[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[jj][i] += w[i];
+              }
+            }
+          }
+          if (sg == nseg - 1) {           // correction accumulator of this tile (complete with the last segment)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+              const int j = half + jj * CHUNK_STEP;
+              if (j < BN / 32) {
+                float w[32];
+                tmem_ld_32x32(tmem_base + lane_bits + (2 + (ti & 1)) * BN + j * 32, w);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[jj][i] += w[i];
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(seg_empty_bar + buf);
+        }
+        if (ok) {
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) {
+            const int j = half + jj * CHUNK_STEP;
+            if (j < BN / 32) process_chunk(j, acc[jj]);
+          }
+        }
+      } else {
+        const int buf = g & 1;
+        if (!mbar_wait(seg_full_bar + buf, (g >> 1) & 1, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = half; j < BN / 32; j += CHUNK_STEP) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + lane_bits + buf * BN + j * 32, v);
+          process_chunk(j, v);
+        }
+        tc_fence_before();
+        mbar_arrive(seg_empty_bar + buf);
+        ++g;
       }
-      // this thread is done reading the accumulator buffer: hand it back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(tmem_empty_bar + ab);
       if (half == 0) epilogue_head(e, img, r, head_acc);
     }
-    // NaN compares false against everything: !(amax <= 65504) also catches it when it reaches amax via fabsf/fmaxf of inf
+    // NaN compares false against everything, inf exceeds the bound
     if (!(amax <= 65504.f) && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
   }
   tc_fence_before();
