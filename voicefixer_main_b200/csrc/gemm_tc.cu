@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int it = 0;
+      int s = 0;              // ring slot and its phase bit advance by increment: no division on the issue path
+      uint32_t ph = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const int nt = tile % n_tiles, mt = tile / n_tiles;
@@ -142,9 +143,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
           const GemmTap tap = pr.taps[t];
           const bool a_lo = THREE || tap.both;
           const uint32_t tx = (a_lo ? 2u : 1u) * A_BYTES + (THREE ? 2u : 1u) * B_BYTES;
-          for (int c = 0; c < tap.nch; c += BK, ++it) {
-            const int s = it % stages;
-            const uint32_t ph = (it / stages) & 1;
+          for (int c = 0; c < tap.nch; c += BK) {
             if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(full_bar + s, tx);
@@ -152,6 +151,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             tma_load_2d(st + off_b, &P.b_hi, full_bar + s, tap.k_off + c, n0);
             if (a_lo) tma_load_3d(st + A_BYTES, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
             if (THREE) tma_load_2d(st + off_b + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
+            if (++s == stages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -161,25 +161,25 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
-      int it = 0, ti = 0, g = 0;      // smem chunk counter, tile counter, accumulation-segment counter
+      int s = 0, ti = 0, g = 0;       // smem ring slot, tile counter, accumulation-segment counter
+      uint32_t ph = 0;                // phase bit of the ring slot
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
         const uint32_t d_corr = tmem_base + (2 + (ti & 1)) * BN;
         uint32_t d_main = 0, m_started = 0, c_started = 0;
-        int ci = 0, buf = 0;
+        int left_in_tile = tile_chunks, left_in_seg = 0, buf = 0;   // countdowns: no division on the issue path
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const int nch = pr.taps[t].nch;
           const bool both = pr.taps[t].both != 0;
-          for (int c = 0; c < nch; c += BK, ++it) {
-            if (ci % seg_chunks == 0) {          // open a segment: its accumulator buffer must have been drained
+          for (int c = 0; c < nch; c += BK) {
+            if (left_in_seg == 0) {              // open a segment: its accumulator buffer must have been drained
+              left_in_seg = min(seg_chunks, left_in_tile);
               buf = g & 1;
               if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
               tc_fence_after();
               d_main = tmem_base + buf * BN;
               m_started = 0;
             }
-            const int s = it % stages;
-            const uint32_t ph = (it / stages) & 1;
             if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
@@ -201,8 +201,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
               }
             }
             umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
-            ++ci;
-            if (ci % seg_chunks == 0 || ci == tile_chunks) {   // close the segment
+            if (++s == stages) { s = 0; ph ^= 1; }
+            --left_in_tile;
+            if (--left_in_seg == 0) {            // close the segment
               umma_commit(seg_full_bar + buf);
               ++g;
             }
