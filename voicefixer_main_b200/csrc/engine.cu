@@ -434,7 +434,7 @@ int load_all(vf_ctx* ctx) {
       const std::string p = "vocoder.res." + std::to_string(s) + "." + std::to_string(i);
       NEED(wa, p + ".a.weight"); NEED(ba, p + ".a.bias"); NEED(wb, p + ".b.weight"); NEED(bb, p + ".b.bias");
       rc = pack_conv1d(ctx, &ctx->voc_res_a[s][i], *wa, *ba); if (rc) return rc;
-      rc = pack_conv1d(ctx, &ctx->voc_res_b[s][i], *wb, *bb, true); if (rc) return rc;
+      rc = pack_conv1d(ctx, &ctx->voc_res_b[s][i], *wb, *bb, (int)wb->shape[0] <= 128); if (rc) return rc;
     }
   }
   {
@@ -616,7 +616,7 @@ struct Builder {
       const double out_elems = (double)n_img * (epi.map == MAP_CONVT1D ? (double)epi.out_rows_valid * epi.cout
                                                 : (epi.map == MAP_CONVT2D ? 4.0 * epi.rows_in * epi.cout : (double)epi.rows_in * N));
       op.bytes = a_elems * (terms == 3 ? 4 : 2) + (double)W.N * W.K * (terms == 3 ? 4 : 2) +
-                 out_elems * ((epi.out_raw ? 4 : 0) + (epi.out_r.hi ? 4 : 0) + (epi.out_a.hi ? 4 : 0) + (epi.resid ? 4 : 0));
+                 out_elems * ((epi.out_raw ? 4 : 0) + (epi.out_r.hi ? 4 : 0) + (epi.out_a.hi ? (terms == 3 ? 4 : 2) : 0) + ((epi.resid || epi.resid_hi) ? 4 : 0));
       snprintf(op.label, sizeof op.label, "%s", label.c_str());
     }
     ops.push_back(op);
@@ -915,9 +915,17 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         set_out_a(e, dst, 0, nullptr, nullptr, ACT_LRELU, last ? c.voc_stage_slope : c.voc_res_slope);
         b.label = "voc.res" + std::to_string(s) + "." + std::to_string(i) + ".b";
         std::vector<GemmTap> taps = taps1d(3, 1, cout, true);
-        taps.push_back(GemmTap{0, 1, 0, 0, cout, 1});          // x itself: identity weights, both planes
         ASrc xsrc{xr[curx], (int)L, 0};
-        b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, &xsrc, taps, e, B, terms);
+        if (cout <= 128) {
+          // load/store-bound stacks: x rides through the accumulator (identity weights, both planes) and the
+          // epilogue issues no global loads
+          taps.push_back(GemmTap{0, 1, 0, 0, cout, 1});
+          b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, &xsrc, taps, e, B, terms);
+        } else {
+          // MMA-bound stacks: the identity tap would add ~40% tensor work; add the planes in the epilogue instead
+          e.resid_hi = xr[curx].p.hi; e.resid_lo = xr[curx].p.lo; e.resid_ld = cout;
+          b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, nullptr, taps, e, B, terms);
+        }
         curx = 1 - curx;
       }
     }

@@ -62,6 +62,8 @@ struct GemmEpilogue {
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [n_img * rows_in, resid_ld] or null (MAP_PLAIN only)
   int resid_ld;
+  const __half* resid_hi;  // residual given as hi/lo planes [n_img * rows_in, resid_ld] (vocoder stacks whose
+  const __half* resid_lo;  // GEMM is MMA-bound: cheaper to add in the epilogue than as an identity tap)
   float* out_raw;      // fp32 or null
   int raw_ld;
   OutPlane out_r;      // raw value split hi/lo (consumed by 1x1 shortcut taps)
@@ -157,6 +159,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int img, i
       const float4 q = __ldg(rp + i);
       v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
     }
+  }
+  if (e.resid_hi) {
+    const size_t ro = ((size_t)img * e.rows_in + r) * e.resid_ld + co0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __half2float(e.resid_hi[ro + i]) + __half2float(e.resid_lo[ro + i]);
   }
   if (pad) {
 #pragma unroll

@@ -186,18 +186,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             const uint32_t a_lo = a_hi + A_BYTES;
             const uint32_t b_hi = a_hi + off_b;
             const uint32_t b_lo = b_hi + B_BYTES;
+            // descriptors differ only in the 14-bit start-address field: +2 (x16 B) per 32-byte K step
+            const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), db_hi0 = make_smem_desc(b_hi, ROW_BYTES);
+            const uint64_t da_lo0 = make_smem_desc(a_lo, ROW_BYTES), db_lo0 = make_smem_desc(b_lo, ROW_BYTES);
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k) {
-              const uint64_t da_hi = make_smem_desc(a_hi + k * 32, ROW_BYTES);
-              const uint64_t db_hi = make_smem_desc(b_hi + k * 32, ROW_BYTES);
-              umma_f16(d_main, da_hi, db_hi, idesc, m_started);
+              umma_f16(d_main, da_hi0 + 2 * k, db_hi0 + 2 * k, idesc, m_started);
               m_started = 1;
               if (THREE) {
-                umma_f16(d_corr, da_hi, make_smem_desc(b_lo + k * 32, ROW_BYTES), idesc, c_started);
+                umma_f16(d_corr, da_hi0 + 2 * k, db_lo0 + 2 * k, idesc, c_started);
                 c_started = 1;
-                umma_f16(d_corr, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
+                umma_f16(d_corr, da_lo0 + 2 * k, db_hi0 + 2 * k, idesc, 1u);
               } else if (both) {
-                umma_f16(d_main, make_smem_desc(a_lo + k * 32, ROW_BYTES), db_hi, idesc, 1u);
+                umma_f16(d_main, da_lo0 + 2 * k, db_hi0 + 2 * k, idesc, 1u);
               }
             }
             umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     const int map = e.map, Wp = e.Wp, cout = e.cout, rows_in = e.rows_in;
     const bool has_affine = e.a_scale != nullptr, has_bias = e.bias != nullptr;
     const bool want_a = e.out_a.hi != nullptr, want_r = e.out_r.hi != nullptr, want_raw = e.out_raw != nullptr;
-    const bool has_resid = e.resid != nullptr, has_head = e.head_w != nullptr;
+    const bool has_resid = e.resid != nullptr, has_resid_planes = e.resid_hi != nullptr, has_head = e.head_w != nullptr;
     const int act = e.act;
     const float slope = e.slope;
     // lane roles for the row-major global accesses
@@ -321,6 +322,34 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
           for (int i = 0; i < 8; ++i) {
             const float4 x = stg_f[sw128(lane, i)];
             v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          }
+        }
+        if (has_resid_planes) {           // residual stream kept as hi/lo planes: coalesced load, sum in fp32
+          const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + h_row;
+            uint4 xh = make_uint4(0, 0, 0, 0), xl = make_uint4(0, 0, 0, 0);
+            if (m0 + q * 32 + rr < rows_in) {
+              xh = __ldg(reinterpret_cast<const uint4*>(e.resid_hi + rbase + (size_t)rr * e.resid_ld) + h_c16);
+              xl = __ldg(reinterpret_cast<const uint4*>(e.resid_lo + rbase + (size_t)rr * e.resid_ld) + h_c16);
+            }
+            stg_h[sw64(rr, h_c16)] = xh;
+            stg_l[sw64(rr, h_c16)] = xl;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 xh = stg_h[sw64(lane, i)], xl = stg_l[sw64(lane, i)];
+            const __half2* ph = reinterpret_cast<const __half2*>(&xh);
+            const __half2* pl = reinterpret_cast<const __half2*>(&xl);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 fh = __half22float2(ph[k]), fl = __half22float2(pl[k]);
+              v[8 * i + 2 * k] += fh.x + fl.x;
+              v[8 * i + 2 * k + 1] += fh.y + fl.y;
+            }
           }
         }
         const bool pad = (flags & kRowPad) != 0;
