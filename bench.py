@@ -231,23 +231,39 @@ def run_b200(args):
     groups = {}
     for r in prof:
         if r["bn"]:
-            g = groups.setdefault((r["bn"], r["bk"]), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
-            g["ms"] += r["ms"]; g["flops"] += r["flops"]; g["bytes"] += r["bytes"]; g["n"] += 1
+            g = groups.setdefault((r["bn"], r["bk"], r.get("terms", 0)), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0, "labels": []})
+            g["ms"] += r["ms"]; g["flops"] += r["flops"]; g["bytes"] += r["bytes"]; g["n"] += 1; g["labels"].append(r["label"])
     total_ms = sum(r["ms"] for r in prof)
-    (bn, bk), top = max(groups.items(), key=lambda kv: kv[1]["ms"])
-    achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
-    hbm_floor = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+
+    def rates(g):
+        tf = g["flops"] / (g["ms"] * 1e-3) / 1e12
+        gb = g["bytes"] / (g["ms"] * 1e-3) / 1e9
+        return tf, gb, tf / peaks["tflops"], gb / peaks["hbm_gbs"]
+
+    (bn, bk, terms), top = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    tf, gb, f_t, f_h = rates(top)
+    bound = "hbm" if f_h > f_t else "tensor"
+    # dram__bytes of the matching ncu --set full capture (profiles/traffic.json, written by tools/summarize_profiles.py)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        for lab in top["labels"]:
+            if lab in tj:
+                traffic = {"label": lab, "dram_bytes_per_launch": tj[lab]["dram_bytes"], "algorithmic_bytes_per_launch": top["bytes"] / top["n"]}
+                break
     roofline = {
-        "kernel": f"gemm_tc_kernel<{bn},{bk}> (tcgen05 flat-shift conv GEMM)", "bound": "tensor",
-        "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-        "peak_source": peaks["source"] + " bf16 dense (== fp16 rate), sustained",
-        "traffic": None, "launches": top["n"], "avg_launch_ms": top["ms"] / top["n"],
-        "share_of_step": top["ms"] / total_ms,
-        "algorithmic_gflop_per_launch": top["flops"] / top["n"] / 1e9,
-        
-        "min_hbm_gbs_at_this_time": hbm_floor, "hbm_frac_of_peak": hbm_floor / peaks["hbm_gbs"],
-        "all_kernels": {f"gemm<{k[0]},{k[1]}>": {"ms": v["ms"], "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "launches": v["n"]}
-                        for k, v in groups.items()},
+        "kernel": f"gemm_tc_kernel<BN={bn},BK={bk},{'3-term' if terms == 3 else 'hi-only'}> (tcgen05 flat-shift conv GEMM; layers: {top['labels'][0]} ... {top['labels'][-1]})",
+        "bound": bound,
+        "achieved": gb if bound == "hbm" else tf, "peak": peaks["hbm_gbs"] if bound == "hbm" else peaks["tflops"],
+        "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": f_h if bound == "hbm" else f_t,
+        "peak_source": peaks["source"] + (" STREAM copy" if bound == "hbm" else " bf16 dense (== fp16 rate), sustained"),
+        "traffic": traffic, "launches": top["n"], "avg_launch_ms": top["ms"] / top["n"], "share_of_step": top["ms"] / total_ms,
+        "algorithmic_gflop_per_launch": top["flops"] / top["n"] / 1e9, "algorithmic_gb_per_launch": top["bytes"] / top["n"] / 1e9,
+        "tensor_frac": f_t, "hbm_frac": f_h,
+        "all_kernels": {f"gemm<{k[0]},{k[1]},{'3t' if k[2] == 3 else '1t'}>": {"ms": v["ms"], "launches": v["n"], "tflops": rates(v)[0], "min_gbs": rates(v)[1],
+                                                                   "tensor_frac": rates(v)[2], "hbm_frac": rates(v)[3]}
+                        for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
     }
     slow = sorted(prof, key=lambda r: -r["ms"])[:8]
     clips = B * world

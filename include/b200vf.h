@@ -140,11 +140,11 @@ VF_API int vf_stage_times(vf_ctx* ctx, float ms[4]);
 /* Per-launch profile: with op timing enabled, the next vf_restore records a CUDA event before every kernel of
  * the UNet and vocoder launch chains.  vf_op_info(i) synchronises and returns the device time of launch i
  * together with its ALGORITHMIC flops / minimum HBM bytes (the reference op's own counts), the tcgen05 tile
- * (bn, bk; 0 for non-GEMM kernels) and a label such as "enc3.b2.conv1".  For roofline reporting only. */
+ * (bn, bk, fp16 split terms; 0 for non-GEMM kernels) and a label such as "enc3.b2.conv1".  For roofline reporting only. */
 VF_API int vf_enable_op_timing(vf_ctx* ctx, int enable);
 VF_API int vf_op_count(vf_ctx* ctx);
-VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, char* label,
-                      int label_cap);
+VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, int* terms,
+                      char* label, int label_cap);
 
 /* Self-test of one flat-shift GEMM configuration: random fp16 hi/lo planes through the tcgen05 kernel and
  * the SIMT validation kernel; returns max |difference| and max |value|.  Synchronous. */

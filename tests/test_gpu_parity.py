@@ -236,6 +236,28 @@ def test_long_form_segment_loop(model, state, monkeypatch):
     assert torch.equal(out[:, 44100 * 60:], tail)      # segments are independent: the tail is its own restore
 
 
+@pytest.mark.parametrize("batch,n", [(1, 1025), (5, 28224), (3, 2 * 44100 + 123)])
+def test_restore_edge_shapes_vs_oracle(model, state, batch, n):
+    """Minimum length the reflect pad allows (T = 3 -> T' = 64), T an exact multiple of 64 (28224 / 441 = 64 -> T = 65),
+    odd batch, ragged length: stage B log-mel and final waveform against the oracle."""
+    wav = O.synth_clips(batch, n, seed=100 + batch)
+    st = {}
+    with torch.no_grad():
+        ref = O.restore(state, wav, exact_stft=True, stages=st)
+    out = model.restore(wav.cuda()).cpu()
+    eng = model._engine()
+    eng.check_errors()
+    mel, log_mel = eng.restore_stages(batch, n)
+    assert out.shape == (batch, n) and log_mel.shape == (batch, 1 + n // 441, 128)
+    ref_mel = st["mel_noisy"][0][:, 0].float()
+    assert float((mel.cpu() - ref_mel).abs().max()) < 5e-6 * float(ref_mel.max())
+    assert float((out - ref).pow(2).mean().sqrt()) < WAV_RMS_TOL
+    # stage B on the *same* mel input (the e2e log-mel also carries the front ends' fp32 noise in quiet bins)
+    with torch.no_grad():
+        ref_lm = O.generator_forward(state, mel.cpu()[:, None])
+    assert float((log_mel.cpu() - ref_lm[:, 0]).abs().max()) < MEL_TOL
+
+
 def test_host_entry_point_and_launch_count(model):
     wav = O.synth_clips(2, 8820, seed=8)
     pin_in, pin_out = wav.pin_memory(), torch.empty_like(wav).pin_memory()

@@ -78,6 +78,20 @@ if reps:
                 if any(k in h for k in ("dram__", "lts__t", "lts__throughput", "tensor", "sm__throughput", "warps_active", "launch__", "gpu__time",
                                         "xbar2l1tex_read_bytes.sum", "smsp__inst_executed.sum", "smsp__cycles_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")):
                     w.writerow([h, d[h][1], d[h][0]])
+    # label -> dram traffic of the captured launch, for bench.py's roofline.traffic
+    def _bytes(v, u):
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    traffic = {}
+    for name, d in table:
+        label = name.replace("voc_res", "voc.res").replace("_conv", ".conv")
+        parts = name.split("_")
+        if name.startswith("voc_res"):
+            label = f"voc.res{parts[1][3:]}.{parts[2]}.{parts[3]}"
+        else:
+            label = f"{parts[0]}.{parts[1]}.{parts[2]}"
+        traffic[label] = {"kernel": d["Kernel Name"][0], "dram_bytes": _bytes(*d["dram__bytes_read.sum"]) + _bytes(*d["dram__bytes_write.sum"]),
+                          "time_us": d["gpu__time_duration.sum"][0] + " " + d["gpu__time_duration.sum"][1]}
+    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     out += ["| metric | " + " | ".join(n for n, _ in table) + " |", "|---|" + "---|" * len(table)]
     out.append("| kernel | " + " | ".join(re.sub(r"\(.*", "", d["Kernel Name"][0]).replace("void ", "") for _, d in table) + " |")
     for m in WANT:

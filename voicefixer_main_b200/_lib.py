@@ -86,7 +86,7 @@ def load_library():
     lib.vf_enable_op_timing.argtypes = [P, c_int]
     lib.vf_op_count.argtypes = [P]
     lib.vf_op_info.argtypes = [P, c_int, POINTER(c_float), POINTER(c_double), POINTER(c_double), POINTER(c_int),
-                               POINTER(c_int), c_char_p, c_int]
+                               POINTER(c_int), POINTER(c_int), c_char_p, c_int]
     _lib = lib
     return lib
 

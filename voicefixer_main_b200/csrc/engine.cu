@@ -151,7 +151,7 @@ struct vf_ctx {
   int voc_last_c = 64;
   std::map<std::pair<int, long>, std::unique_ptr<Plan>> plans;
   bool op_timing = false;
-  struct ProfRec { std::string label; double flops, bytes; int bn, bk; };
+  struct ProfRec { std::string label; double flops, bytes; int bn, bk, terms; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_ev;
   bool timing = false;
@@ -1003,7 +1003,7 @@ int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
       int rc = prof_mark(ctx, st);
       if (rc) return rc;
       const char* kinds[] = {"gemm", "unet_first", "pool", "voc_condition", "reflect_fill", "voc_tail", "finalize", "memset"};
-      ctx->prof.push_back({op.label[0] ? std::string(op.label) : std::string(kinds[op.kind]), op.flops, op.bytes, op.bn, op.bk});
+      ctx->prof.push_back({op.label[0] ? std::string(op.label) : std::string(kinds[op.kind]), op.flops, op.bytes, op.bn, op.bk, op.kind == OP_GEMM ? op.tc.prob.terms : 0});
     }
     switch (op.kind) {
       case OP_GEMM:
@@ -1356,7 +1356,7 @@ VF_API int vf_enable_op_timing(vf_ctx* ctx, int enable) {
   return VF_OK;
 }
 VF_API int vf_op_count(vf_ctx* ctx) { return ctx ? (int)ctx->prof.size() : -1; }
-VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, char* label, int label_cap) {
+VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, int* terms, char* label, int label_cap) {
   if (!ctx || i < 0 || i >= (int)ctx->prof.size()) return VF_EINVAL;
   // records of the frontend / finalize launches are not tracked; record i spans events [i, i+1) except that
   // each run_ops() call appends one closing event after its last op, so consecutive event pairs stay aligned
@@ -1370,6 +1370,7 @@ VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* byte
   if (bytes) *bytes = ctx->prof[i].bytes;
   if (bn) *bn = ctx->prof[i].bn;
   if (bk) *bk = ctx->prof[i].bk;
+  if (terms) *terms = ctx->prof[i].terms;
   if (label && label_cap > 0) snprintf(label, label_cap, "%s", ctx->prof[i].label.c_str());
   return VF_OK;
 }

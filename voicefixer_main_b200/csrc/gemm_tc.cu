@@ -12,9 +12,9 @@
 // Accumulation precision.  The tensor core adds into its fp32 accumulator with truncation, so one long chain
 // of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with one accumulator per
 // tile).  In 3-term mode the K loop is therefore cut into segments of 16 MMAs that ping-pong between two TMEM
-// accumulators; the epilogue warps add each finished segment into registers in fp32 round-to-nearest
-// ("promotion") while the tensor core already works on the next one, and the two small correction products
-// (hi*lo, lo*hi) accumulate in a third, per-tile accumulator.  The same ping-pong is the tile double buffering
+// accumulator buffers; the epilogue warps add each finished segment into registers in fp32 round-to-nearest
+// ("promotion") while the tensor core already works on the next one.  Each buffer is [main | correction]: the
+// two small correction products (hi*lo, lo*hi) never mix into the main chain.  The same ping-pong is the tile double buffering
 // of the 1-term mode (one segment per tile): tile i+1 accumulates while tile i drains.
 //
 // Epilogue I/O.  A thread owns a row, but global stores are issued row-major by the whole warp: values are
@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   const int total_tiles = pr.n_img * pr.m_tiles * n_tiles;
   const int tile_chunks = P.tile_chunks;                 // K chunks per tile
   const int seg_chunks = THREE ? P.seg_chunks : tile_chunks;   // K chunks per accumulation segment
-  // TMEM columns: main ping-pong M0 [0,BN) M1 [BN,2BN); THREE: correction accumulators C0 [2BN,3BN) C1 [3BN,4BN)
+  // TMEM columns: accumulator buffers ping-pong.  1-term: M0 [0,BN) M1 [BN,2BN).  3-term: [M0|C0] [M1|C1], each
+  // 2*BN wide: hi*hi and hi*lo come from ONE MMA of width 2*BN against the stacked [B_hi; B_lo] tile (A_hi is read
+  // from shared memory once instead of twice), lo*hi is a second MMA of width BN into the C half.
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -161,12 +163,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+      constexpr uint32_t idesc2 = make_idesc_f16(GEMM_BM, THREE ? 2 * BN : BN);   // hi x [hi | lo]
+      constexpr int ACC_W = THREE ? 2 * BN : BN;
       int s = 0, ti = 0, g = 0;       // smem ring slot, tile counter, accumulation-segment counter
       uint32_t ph = 0;                // phase bit of the ring slot
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
-        const uint32_t d_corr = tmem_base + (2 + (ti & 1)) * BN;
-        uint32_t d_main = 0, m_started = 0, c_started = 0;
+        uint32_t d_main = 0, m_started = 0;
         int left_in_tile = tile_chunks, left_in_seg = 0, buf = 0;   // countdowns: no division on the issue path
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const int nch = pr.taps[t].nch;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
               buf = g & 1;
               if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
               tc_fence_after();
-              d_main = tmem_base + buf * BN;
+              d_main = tmem_base + buf * ACC_W;
               m_started = 0;
             }
             if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
@@ -188,15 +191,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             const uint32_t b_lo = b_hi + B_BYTES;
             // descriptors differ only in the 14-bit start-address field: +2 (x16 B) per 32-byte K step
             const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), db_hi0 = make_smem_desc(b_hi, ROW_BYTES);
-            const uint64_t da_lo0 = make_smem_desc(a_lo, ROW_BYTES), db_lo0 = make_smem_desc(b_lo, ROW_BYTES);
+            const uint64_t da_lo0 = make_smem_desc(a_lo, ROW_BYTES);
+            (void)b_lo;   // the lo weight tile sits right behind the hi tile: one descriptor spans [B_hi; B_lo]
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k) {
-              umma_f16(d_main, da_hi0 + 2 * k, db_hi0 + 2 * k, idesc, m_started);
+              umma_f16(d_main, da_hi0 + 2 * k, db_hi0 + 2 * k, idesc2, m_started);
               m_started = 1;
               if (THREE) {
-                umma_f16(d_corr, da_hi0 + 2 * k, db_lo0 + 2 * k, idesc, c_started);
-                c_started = 1;
-                umma_f16(d_corr, da_lo0 + 2 * k, db_hi0 + 2 * k, idesc, 1u);
+                umma_f16(d_main + BN, da_lo0 + 2 * k, db_hi0 + 2 * k, idesc, 1u);
               } else if (both) {
                 umma_f16(d_main, da_lo0 + 2 * k, db_hi0 + 2 * k, idesc, 1u);
               }
@@ -455,26 +457,15 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
           for (int jj = 0; jj < NJ; ++jj) {
             const int j = half + jj * CHUNK_STEP;
             if (j < BN / 32) {
-              float w[32];
-              tmem_ld_32x32(tmem_base + lane_bits + buf * BN + j * 32, w);
+              float w[32], c[32];
+              tmem_ld_32x32(tmem_base + lane_bits + buf * 2 * BN + j * 32, w);
+              tmem_ld_32x32(tmem_base + lane_bits + buf * 2 * BN + BN + j * 32, c);
               if (sg == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[jj][i] = w[i];
+                for (int i = 0; i < 32; ++i) acc[jj][i] = w[i] + c[i];
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[jj][i] += w[i];
-              }
-            }
-          }
-          if (sg == nseg - 1) {           // correction accumulator of this tile (complete with the last segment)
-#pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) {
-              const int j = half + jj * CHUNK_STEP;
-              if (j < BN / 32) {
-                float w[32];
-                tmem_ld_32x32(tmem_base + lane_bits + (2 + (ti & 1)) * BN + j * 32, w);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) acc[jj][i] += w[i];
+                for (int i = 0; i < 32; ++i) acc[jj][i] += w[i] + c[i];
               }
             }
           }
