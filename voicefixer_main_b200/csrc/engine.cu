@@ -25,7 +25,7 @@
 
 namespace vf {
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms);
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax);
 cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
 }  // namespace vf
 
@@ -475,10 +475,10 @@ struct Builder {
     return pl;
   }
 
-  int make_map3(CUtensorMap* m, const __half* base, int C, int rows, int img_rows, int n_img, int box_c, bool sw128) {
+  int make_map3(CUtensorMap* m, const __half* base, int C, int rows, int img_rows, int n_img, int box_c, bool sw128, int box_rows) {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_img};
     cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)img_rows * C * 2};
-    cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)GEMM_BM, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -537,8 +537,42 @@ struct Builder {
       t.k_off = k;
       const int padded = round_up(t.nch, bk);
       k += padded;
+      t.g = 1; t.shift[0] = t.shift[1] = t.shift[2] = 0; t.kstride = padded;
       if (ctx->validate_simt == 0) t.nch = padded;
     }
+    // Halo groups: up to 3 consecutive taps reading row-adjacent windows of the same planes share one A load of
+    // 128 + 2 rows; each tap is then an MMA on a row-shifted view (tools/probe_desc_shift.cu).  Worth it where the
+    // layer is bound by shared-memory / L2 feed traffic (narrow N); wide-N tiles keep the finer-grained ring.
+    int gmax = 1;
+    {
+      bool want = ctx->validate_simt == 0 && bn <= 64;
+      if (const char* ov = getenv("VF_TUNE_HALO")) want = ctx->validate_simt == 0 && atoi(ov) != 0 && (atoi(ov) > 1 || bn <= 64);
+      if (want) {
+        std::vector<GemmTap> grouped;
+        for (size_t i = 0; i < taps.size();) {
+          GemmTap gt = taps[i];
+          size_t n = 1;
+          int step = 0;
+          while (n < 3 && i + n < taps.size()) {
+            const GemmTap& a = taps[i + n - 1];
+            const GemmTap& b2 = taps[i + n];
+            const int d = b2.a_off - a.a_off;
+            if (b2.src != gt.src || b2.c_off != gt.c_off || b2.nch != gt.nch || b2.both || gt.both || (d != 1 && d != -1)) break;
+            if (n == 1) step = d; else if (d != step) break;
+            ++n;
+          }
+          const int lo = std::min(taps[i].a_off, taps[i + n - 1].a_off);
+          for (size_t j = 0; j < n; ++j) gt.shift[j] = taps[i + j].a_off - lo;
+          gt.a_off = lo;
+          gt.g = (int)n;
+          gmax = std::max(gmax, gt.g);
+          grouped.push_back(gt);
+          i += n;
+        }
+        taps.swap(grouped);
+      }
+    }
+    const int a_box_rows = gmax > 1 ? GEMM_BM + 2 : GEMM_BM;
     if (k != W.K) { rc = fail(ctx, VF_EINVAL, "GEMM K mismatch: taps cover %d, packed weight has %d", k, W.K); return; }
     GemmProblem pr;
     memset(&pr, 0, sizeof pr);
@@ -574,14 +608,17 @@ struct Builder {
       const ASrc* srcs[2] = {&s0, s1 ? s1 : &s0};
       for (int i = 0; i < 2 && !rc; ++i) {
         const size_t off = (size_t)srcs[i]->row0 * srcs[i]->pl.C;
-        rc = make_map3(&tp.a_hi[i], srcs[i]->pl.p.hi + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64);
-        if (!rc) rc = make_map3(&tp.a_lo[i], srcs[i]->pl.p.lo + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64);
+        rc = make_map3(&tp.a_hi[i], srcs[i]->pl.p.hi + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64, a_box_rows);
+        if (!rc) rc = make_map3(&tp.a_lo[i], srcs[i]->pl.p.lo + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64, a_box_rows);
       }
       if (!rc) rc = make_map2(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
       if (!rc) rc = make_map2(&tp.b_lo, W.lo, W.K, N, bk, bn, bk == 64);
       // accumulation segments (see gemm_tc.cu): 16 truncating MMAs per chain, then promotion to registers
-      tp.tile_chunks = k / bk;
-      tp.seg_chunks = std::max(1, 16 / (bk / 16));
+      tp.tile_chunks = 0;
+      for (auto& t : taps) tp.tile_chunks += t.nch / bk;           // ring slots (group chunks) per tile
+      tp.seg_chunks = std::max(1, 16 / ((bk / 16) * gmax));
+      tp.a_box_rows = a_box_rows;
+      tp.gmax = gmax;
       bool any_both = false;
       for (auto& t : taps) any_both |= t.both != 0;
       tp.planes_a = (terms == 3 || any_both) ? 2 : 1;
@@ -596,7 +633,7 @@ struct Builder {
         if (tp.tmem_cols * ctas > 512) continue;
         const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
         for (stages = 8; stages >= 2; --stages)
-          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms) <= per_cta) break;
+          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax) <= per_cta) break;
         if (stages >= 2) break;
       }
       if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }
@@ -607,7 +644,7 @@ struct Builder {
     }
     {   // algorithmic work: the reference op's own MAC count and the minimum HBM traffic of this launch
       double kreal = 0, a_elems = 0;
-      for (auto& t : taps) if (!t.both) kreal += std::min(t.nch, (t.src ? s1 : &s0)->pl.C);
+      for (auto& t : taps) if (!t.both) kreal += (double)t.g * std::min(t.nch, (t.src ? s1 : &s0)->pl.C);
       const double wfrac = (epi.Wp > 1) ? double(epi.Wp - 1) / epi.Wp : 1.0;
       double rows = (double)n_img * (epi.map == MAP_CONVT1D ? epi.rows_in - 1 : epi.rows_in) * wfrac;
       op.flops = 2.0 * rows * N * kreal * (epi.map == MAP_CONVT2D ? 9.0 / 16.0 : 1.0);

@@ -33,14 +33,19 @@ enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_ELU = 2 };
 enum { MAP_PLAIN = 0, MAP_CONVT2D = 1, MAP_CONVT1D = 2 };
 enum { ERR_FP16_OVERFLOW = 100, ERR_PIPE_PRODUCER = 201, ERR_PIPE_MMA = 202, ERR_PIPE_EPILOGUE = 203 };
 
-struct GemmTap {
-  int a_off;   // row offset relative to the output row
+struct GemmTap {   // one tap, or a GROUP of up to 3 taps that read row-adjacent windows of the same source
+  int a_off;   // row offset of the (group's) window start relative to the output row
   int src;     // which A source (0/1)
   int c_off;   // first channel inside the source
-  int k_off;   // first column of this tap's segment in the packed weight matrix
-  int nch;     // channels contracted by this tap (multiple of the kernel's BK)
+  int k_off;   // first column of the (first) tap's segment in the packed weight matrix
+  int nch;     // channels contracted by each tap (multiple of the kernel's BK)
   int both;    // 1: contract hi AND lo planes of A even in 1-term mode (identity tap carrying the fp32-grade
                //    residual stream through the accumulator)
+  int g;       // taps in the group (1..3).  Halo load: the A window (128 + 2 rows) is fetched once and tap i is
+               // an MMA on the view shifted by shift[i] rows - a descriptor whose start address is advanced by
+               // shift * row_bytes; the hardware swizzles on absolute address bits (tools/probe_desc_shift.cu)
+  int shift[3];
+  int kstride; // columns between consecutive taps' weight segments
 };
 
 struct OutPlane {
@@ -98,6 +103,8 @@ struct GemmTcParams {
   int seg_chunks;  // 3-term mode: chunks per accumulation segment (promotion to registers in between)
   int tmem_cols;   // power of two >= 2 * BN (main ping-pong) [+ 2 * BN correction accumulators in 3-term mode]
   int planes_a;    // smem slots per stage for A: 2 when any tap contracts the lo plane
+  int a_box_rows;  // rows per A TMA box: 128, or 130 when taps are grouped (halo)
+  int gmax;        // largest tap group: B slots per stage
   int grid;        // persistent CTAs
   GemmProblem prob;
 };

@@ -67,7 +67,6 @@ __device__ __forceinline__ void pack_hi_lo(const float (&v)[32], uint32_t (&hi)[
 template <int BN, int BK, int EPI_WARPS, bool THREE>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64 ? 2 : 1)))
     gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
-  constexpr int A_BYTES = GEMM_BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int ROW_BYTES = BK * 2;
   constexpr int KSTEPS = BK / 16;
@@ -80,8 +79,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stages = P.stages;
   const int planes_a = P.planes_a;                      // 2 when any tap contracts the lo plane of A
-  const int stage_bytes = planes_a * A_BYTES + (THREE ? 2 : 1) * B_BYTES;
-  const int off_b = planes_a * A_BYTES;
+  constexpr int B_SLOT = (THREE ? 2 : 1) * B_BYTES;      // [B_hi][B_lo] of one tap, contiguous
+  const int a_box_bytes = P.a_box_rows * ROW_BYTES;     // bytes one A TMA box delivers
+  const int a_slot = (a_box_bytes + 1023) & ~1023;      // halo rows spill into one more swizzle atom
+  const int off_b = planes_a * a_slot;
+  const int stage_bytes = off_b + P.gmax * B_SLOT;
   uint8_t* stg_base = smem + (size_t)stages * stage_bytes;          // EPI_WARPS x 4 KB staging
   uint8_t* tail = stg_base + EPI_WARPS * 4096;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -144,15 +146,18 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const GemmTap tap = pr.taps[t];
           const bool a_lo = THREE || tap.both;
-          const uint32_t tx = (a_lo ? 2u : 1u) * A_BYTES + (THREE ? 2u : 1u) * B_BYTES;
+          const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + tap.g * B_SLOT;
           for (int c = 0; c < tap.nch; c += BK) {
             if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(full_bar + s, tx);
             tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-            tma_load_2d(st + off_b, &P.b_hi, full_bar + s, tap.k_off + c, n0);
-            if (a_lo) tma_load_3d(st + A_BYTES, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-            if (THREE) tma_load_2d(st + off_b + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + c, n0);
+            if (a_lo) tma_load_3d(st + a_slot, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
+            for (int gi = 0; gi < tap.g; ++gi) {
+              uint8_t* sb = st + off_b + gi * B_SLOT;
+              tma_load_2d(sb, &P.b_hi, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
+              if (THREE) tma_load_2d(sb + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
+            }
             if (++s == stages) { s = 0; ph ^= 1; }
           }
         }
@@ -174,6 +179,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const int nch = pr.taps[t].nch;
           const bool both = pr.taps[t].both != 0;
+          const int tg = pr.taps[t].g;
+          const int sh0 = pr.taps[t].shift[0], sh1 = pr.taps[t].shift[1], sh2 = pr.taps[t].shift[2];
           for (int c = 0; c < nch; c += BK) {
             if (left_in_seg == 0) {              // open a segment: its accumulator buffer must have been drained
               left_in_seg = min(seg_chunks, left_in_tile);
@@ -186,21 +193,22 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint32_t a_lo = a_hi + A_BYTES;
-            const uint32_t b_hi = a_hi + off_b;
-            const uint32_t b_lo = b_hi + B_BYTES;
-            // descriptors differ only in the 14-bit start-address field: +2 (x16 B) per 32-byte K step
-            const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), db_hi0 = make_smem_desc(b_hi, ROW_BYTES);
-            const uint64_t da_lo0 = make_smem_desc(a_lo, ROW_BYTES);
-            (void)b_lo;   // the lo weight tile sits right behind the hi tile: one descriptor spans [B_hi; B_lo]
+            const uint32_t a_lo = a_hi + a_slot;
+            // descriptors differ only in the 14-bit start-address field (units of 16 B): +2 per 32-byte K step,
+            // +ROW_BYTES/16 per row of halo shift
+            const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), da_lo0 = make_smem_desc(a_lo, ROW_BYTES);
+            for (int gi = 0; gi < tg; ++gi) {
+              const int sh = (gi == 0 ? sh0 : (gi == 1 ? sh1 : sh2)) * (ROW_BYTES / 16);
+              const uint64_t db0 = make_smem_desc(a_hi + off_b + gi * B_SLOT, ROW_BYTES);   // spans [B_hi; B_lo]
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              umma_f16(d_main, da_hi0 + 2 * k, db_hi0 + 2 * k, idesc2, m_started);
-              m_started = 1;
-              if (THREE) {
-                umma_f16(d_main + BN, da_lo0 + 2 * k, db_hi0 + 2 * k, idesc, 1u);
-              } else if (both) {
-                umma_f16(d_main, da_lo0 + 2 * k, db_hi0 + 2 * k, idesc, 1u);
+              for (int k = 0; k < KSTEPS; ++k) {
+                umma_f16(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, idesc2, m_started);
+                m_started = 1;
+                if (THREE) {
+                  umma_f16(d_main + BN, da_lo0 + sh + 2 * k, db0 + 2 * k, idesc, 1u);
+                } else if (both) {
+                  umma_f16(d_main, da_lo0 + sh + 2 * k, db0 + 2 * k, idesc, 1u);
+                }
               }
             }
             umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
@@ -509,15 +517,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
 // ---------------------------------------------------------------------------------------------- host side
 static int epi_warps_for(int bn) { return bn == 32 ? 4 : 8; }
 
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms) {
-  const size_t stage = (size_t)planes_a * GEMM_BM * bk * 2 + (size_t)(terms == 3 ? 2 : 1) * bn * bk * 2;
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax) {
+  const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
+  const size_t stage = planes_a * a_slot + (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2;
   const int ew = epi_warps_for(bn);
   return stages * stage + ew * 4096 + (2 * stages + 4) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
 }
 
 template <int BN, int BK, int EW, bool THREE>
 static cudaError_t launch_cfg(const GemmTcParams& p, cudaStream_t stream) {
-  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms);
+  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW, THREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
