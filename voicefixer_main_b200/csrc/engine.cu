@@ -25,7 +25,7 @@
 
 namespace vf {
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax);
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes);
 cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
 }  // namespace vf
 
@@ -630,12 +630,30 @@ struct Builder {
       int ctas = (k <= 1024) ? reg_limit : 1;
       if (const char* ov = getenv("VF_TUNE_SMALLK_CTAS")) { if (k <= 1024) ctas = std::max(1, std::min(reg_limit, atoi(ov))); }
       int stages = 0;
-      for (; ctas >= 1; --ctas) {
+      // weight-stationary: one N tile, load/store-bound layer, weights + a ring of >= 2 tiles of activations fit
+      int n_wslots = 0;
+      for (auto& t : taps) n_wslots += (t.nch / bk) * t.g;
+      const int w_bytes = n_wslots * (terms == 3 ? 2 : 1) * bn * bk * 2;
+      bool w_res = N == bn && k <= 1024 && w_bytes <= 100 * 1024 && terms == 1;
+      if (const char* ov = getenv("VF_TUNE_WRES")) w_res = N == bn && k <= 1024 && w_bytes <= 100 * 1024 && (atoi(ov) == 2 || (atoi(ov) == 1 && terms == 1));
+      if (w_res) {
+        for (stages = 16; stages >= 2; --stages)
+          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, w_bytes) <= (size_t)226 * 1024) break;
+        if (stages >= std::min(2 * tp.tile_chunks, 6)) {
+          ctas = 1;
+          tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
+        } else {
+          w_res = false;
+        }
+      }
+      tp.w_resident = w_res ? 1 : 0;
+      tp.w_bytes = w_res ? w_bytes : 0;
+      for (; !w_res && ctas >= 1; --ctas) {
         tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
         if (tp.tmem_cols * ctas > 512) continue;
         const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
         for (stages = 8; stages >= 2; --stages)
-          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax) <= per_cta) break;
+          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, 0) <= per_cta) break;
         if (stages >= 2) break;
       }
       if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }

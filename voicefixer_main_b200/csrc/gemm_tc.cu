@@ -83,14 +83,17 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   const int a_box_bytes = P.a_box_rows * ROW_BYTES;     // bytes one A TMA box delivers
   const int a_slot = (a_box_bytes + 1023) & ~1023;      // halo rows spill into one more swizzle atom
   const int off_b = planes_a * a_slot;
-  const int stage_bytes = off_b + P.gmax * B_SLOT;
-  uint8_t* stg_base = smem + (size_t)stages * stage_bytes;          // EPI_WARPS x 4 KB staging
+  const bool w_res = P.w_resident != 0;
+  const int stage_bytes = off_b + (w_res ? 0 : P.gmax * B_SLOT);
+  uint8_t* w_base = smem + (size_t)stages * stage_bytes;            // resident weights (w_resident), else empty
+  uint8_t* stg_base = w_base + P.w_bytes;                           // EPI_WARPS x 4 KB staging
   uint8_t* tail = stg_base + EPI_WARPS * 4096;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* seg_full_bar = empty_bar + stages;           // [2] main accumulator buffer holds a finished segment
   uint64_t* seg_empty_bar = seg_full_bar + 2;            // [2] ... has been drained by every epilogue thread
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(seg_empty_bar + 2);
+  uint64_t* w_full_bar = seg_empty_bar + 2;              // resident weights have landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
   float* s_shift = s_scale + BN;                               // [BN]
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
       mbar_init(seg_full_bar + i, 1);
       mbar_init(seg_empty_bar + i, EPI_THREADS);
     }
+    mbar_init(w_full_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
     tma_prefetch_desc(&P.b_hi);
@@ -138,6 +142,18 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
       int s = 0;              // ring slot and its phase bit advance by increment: no division on the issue path
       uint32_t ph = 0;
       bool ok = true;
+      if (w_res) {            // weight-stationary: the single N tile's weights, chunk by chunk in MMA order
+        mbar_expect_tx(w_full_bar, (uint32_t)P.w_bytes);
+        uint8_t* wp = w_base;
+        for (int t = 0; t < pr.ntaps; ++t) {
+          const GemmTap tap = pr.taps[t];
+          for (int c = 0; c < tap.nch; c += BK)
+            for (int gi = 0; gi < tap.g; ++gi, wp += B_SLOT) {
+              tma_load_2d(wp, &P.b_hi, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
+              if (THREE) tma_load_2d(wp + B_BYTES, &P.b_lo, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
+            }
+        }
+      }
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const int nt = tile % n_tiles, mt = tile / n_tiles;
         const int img = mt / pr.m_tiles;
@@ -146,14 +162,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const GemmTap tap = pr.taps[t];
           const bool a_lo = THREE || tap.both;
-          const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + tap.g * B_SLOT;
+          const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + (w_res ? 0 : tap.g * B_SLOT);
           for (int c = 0; c < tap.nch; c += BK) {
             if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(full_bar + s, tx);
             tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
             if (a_lo) tma_load_3d(st + a_slot, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-            for (int gi = 0; gi < tap.g; ++gi) {
+            for (int gi = 0; gi < tap.g && !w_res; ++gi) {
               uint8_t* sb = st + off_b + gi * B_SLOT;
               tma_load_2d(sb, &P.b_hi, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
               if (THREE) tma_load_2d(sb + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
@@ -173,8 +189,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
       int s = 0, ti = 0, g = 0;       // smem ring slot, tile counter, accumulation-segment counter
       uint32_t ph = 0;                // phase bit of the ring slot
       bool ok = true;
+      if (w_res) {
+        ok = mbar_wait(w_full_bar, 0, e.err, ERR_PIPE_MMA);
+        tc_fence_after();
+      }
+      const uint32_t w_addr = smem_u32(w_base);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
         uint32_t d_main = 0, m_started = 0;
+        uint32_t w_cur = w_addr;      // resident weights are consumed in the order they were loaded
         int left_in_tile = tile_chunks, left_in_seg = 0, buf = 0;   // countdowns: no division on the issue path
         for (int t = 0; t < pr.ntaps && ok; ++t) {
           const int nch = pr.taps[t].nch;
@@ -199,7 +221,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
             const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), da_lo0 = make_smem_desc(a_lo, ROW_BYTES);
             for (int gi = 0; gi < tg; ++gi) {
               const int sh = (gi == 0 ? sh0 : (gi == 1 ? sh1 : sh2)) * (ROW_BYTES / 16);
-              const uint64_t db0 = make_smem_desc(a_hi + off_b + gi * B_SLOT, ROW_BYTES);   // spans [B_hi; B_lo]
+              const uint64_t db0 = make_smem_desc(w_res ? w_cur : a_hi + off_b + gi * B_SLOT, ROW_BYTES);   // spans [B_hi; B_lo]
+              w_cur += B_SLOT;
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
                 umma_f16(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, idesc2, m_started);
@@ -517,16 +540,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
 // ---------------------------------------------------------------------------------------------- host side
 static int epi_warps_for(int bn) { return bn == 32 ? 4 : 8; }
 
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax) {
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes) {
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
-  const size_t stage = planes_a * a_slot + (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2;
+  const size_t stage = planes_a * a_slot + (w_bytes ? 0 : (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2);
   const int ew = epi_warps_for(bn);
-  return stages * stage + ew * 4096 + (2 * stages + 4) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
+  return stages * stage + w_bytes + ew * 4096 + (2 * stages + 5) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
 }
 
 template <int BN, int BK, int EW, bool THREE>
 static cudaError_t launch_cfg(const GemmTcParams& p, cudaStream_t stream) {
-  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax);
+  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax, p.w_resident ? p.w_bytes : 0);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW, THREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
