@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
   uint64_t* seg_full_bar = empty_bar + stages;           // [2] main accumulator buffer holds a finished segment
   uint64_t* seg_empty_bar = seg_full_bar + 2;            // [2] ... has been drained by every epilogue thread
   uint64_t* w_full_bar = seg_empty_bar + 2;              // resident weights have landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full_bar + 1);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full_bar + 2);   // keep the float arrays 16-byte aligned
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
   float* s_shift = s_scale + BN;                               // [BN]
@@ -544,7 +544,7 @@ size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, i
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
   const size_t stage = planes_a * a_slot + (w_bytes ? 0 : (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2);
   const int ew = epi_warps_for(bn);
-  return stages * stage + w_bytes + ew * 4096 + (2 * stages + 5) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
+  return stages * stage + w_bytes + ew * 4096 + (2 * stages + 6) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
 }
 
 template <int BN, int BK, int EW, bool THREE>
