@@ -26,6 +26,7 @@
 namespace vf {
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
 size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes);
+void gemm_tc_set_bn64_ew4(bool on);
 cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
 }  // namespace vf
 
@@ -626,7 +627,9 @@ struct Builder {
       tp.planes_a = (terms == 3 || any_both) ? 2 : 1;
       auto pow2 = [](int x) { int c = 32; while (c < x) c *= 2; return c; };
       // occupancy: small-K tiles are bound by loads/stores -> several persistent CTAs per SM; large-K -> one
-      const int reg_limit = bn == 32 ? 3 : (bn == 64 ? 2 : 1);   // matches __launch_bounds__ in gemm_tc.cu
+      const bool ew4 = getenv("VF_TUNE_BN64_EW4") && atoi(getenv("VF_TUNE_BN64_EW4")) != 0;
+      gemm_tc_set_bn64_ew4(ew4);
+      const int reg_limit = bn == 32 ? 3 : (bn == 64 ? ((ew4 && terms == 1) ? 3 : 2) : 1);   // matches __launch_bounds__ in gemm_tc.cu
       int ctas = (k <= 1024) ? reg_limit : 1;
       if (const char* ov = getenv("VF_TUNE_SMALLK_CTAS")) { if (k <= 1024) ctas = std::max(1, std::min(reg_limit, atoi(ov))); }
       int stages = 0;
@@ -634,7 +637,9 @@ struct Builder {
       int n_wslots = 0;
       for (auto& t : taps) n_wslots += (t.nch / bk) * t.g;
       const int w_bytes = n_wslots * (terms == 3 ? 2 : 1) * bn * bk * 2;
-      bool w_res = N == bn && k <= 1024 && w_bytes <= 100 * 1024 && terms == 1;
+      // measured: slower than 2-3 co-resident CTAs streaming weights from L2 (the epilogue, not the ring depth,
+      // limits these layers) - kept as an opt-in experiment (VF_TUNE_WRES=1|2)
+      bool w_res = false;
       if (const char* ov = getenv("VF_TUNE_WRES")) w_res = N == bn && k <= 1024 && w_bytes <= 100 * 1024 && (atoi(ov) == 2 || (atoi(ov) == 1 && terms == 1));
       if (w_res) {
         for (stages = 16; stages >= 2; --stages)

@@ -65,7 +65,7 @@ __device__ __forceinline__ void pack_hi_lo(const float (&v)[32], uint32_t (&hi)[
 }
 
 template <int BN, int BK, int EPI_WARPS, bool THREE>
-__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64 ? 2 : 1)))
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 && EPI_WARPS == 4) ? 3 : (BN == 64 ? 2 : 1)))
     gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int ROW_BYTES = BK * 2;
@@ -538,12 +538,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 ? 3 : (BN == 64
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int epi_warps_for(int bn) { return bn == 32 ? 4 : 8; }
+static bool g_bn64_ew4 = false;   // tuning experiment: BN = 64 hi-only tiles with 4 epilogue warps, 3 CTAs per SM
+void gemm_tc_set_bn64_ew4(bool on) { g_bn64_ew4 = on; }
+static int epi_warps_for(int bn, int terms) { return (bn == 32 || (bn == 64 && terms == 1 && g_bn64_ew4)) ? 4 : 8; }
 
 size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes) {
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
   const size_t stage = planes_a * a_slot + (w_bytes ? 0 : (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2);
-  const int ew = epi_warps_for(bn);
+  const int ew = epi_warps_for(bn, terms);
   return stages * stage + w_bytes + ew * 4096 + (2 * stages + 6) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
 }
 
@@ -568,12 +570,12 @@ cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t s
   if (bk == 64) {
     if (bn == 256) return p.prob.terms == 1 ? launch_cfg<256, 64, 8, false>(p, stream) : cudaErrorInvalidValue;
     if (bn == 128) return launch_one<128, 64, 8>(p, stream);
-    if (bn == 64) return launch_one<64, 64, 8>(p, stream);
+    if (bn == 64) return (p.prob.terms == 1 && g_bn64_ew4) ? launch_cfg<64, 64, 4, false>(p, stream) : launch_one<64, 64, 8>(p, stream);
     if (bn == 32) return launch_one<32, 64, 4>(p, stream);
   } else if (bk == 32) {
     if (bn == 256) return p.prob.terms == 1 ? launch_cfg<256, 32, 8, false>(p, stream) : cudaErrorInvalidValue;
     if (bn == 128) return launch_one<128, 32, 8>(p, stream);
-    if (bn == 64) return launch_one<64, 32, 8>(p, stream);
+    if (bn == 64) return (p.prob.terms == 1 && g_bn64_ew4) ? launch_cfg<64, 32, 4, false>(p, stream) : launch_one<64, 32, 8>(p, stream);
     if (bn == 32) return launch_one<32, 32, 4>(p, stream);
   }
   return cudaErrorInvalidValue;
