@@ -212,79 +212,112 @@ cudaError_t launch_reflect_fill(PlanePtr planes, int batch, int L, int C, int pa
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile = 128 output samples of one clip.  The 134 x C input rows are staged once in shared memory as fp32
-// (coalesced 16-byte loads of the hi / lo planes), then every thread accumulates its 7 x C taps from smem:
-// the 7-fold row reuse never goes back to L1/L2.  Row pitch C + 4 floats keeps the float4 reads conflict-free.
-constexpr int TAIL_TILE = 128;
-__global__ void __launch_bounds__(TAIL_TILE) voc_tail_kernel(VocTailParams p) {
-  extern __shared__ float tail_smem[];
-  const int C = p.C, pitch = C + 4;
-  float* w_s = tail_smem;                       // [7][C]
-  float* x_s = tail_smem + 7 * C;               // [TAIL_TILE + 6][pitch]
+// Tile = 320 output samples of one clip, 5 consecutive samples per thread.  The (320 + 6) x C input rows are
+// copied global -> shared as fp16 with cp.async (no register staging, deep memory-level parallelism).  For each
+// group of 8 channels a thread converts its 11 rows once and reuses them for all 5 outputs x 7 taps, and each
+// weight vector for all 5 outputs: ~5x fewer shared-memory reads per FMA than one-output-per-thread.
+// Row pitch C + 8 halfs = odd multiple of 16 bytes and an odd row stride per thread (5): conflict-free LDS.128.
+constexpr int TAIL_RT = 5, TAIL_THREADS = 64, TAIL_TILE = TAIL_RT * TAIL_THREADS;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <bool THREE>
+__global__ void __launch_bounds__(TAIL_THREADS) voc_tail_kernel(VocTailParams p) {
+  extern __shared__ __align__(16) uint8_t tail_smem[];
+  const int C = p.C, pitch = C + 8;
+  float* w_s = reinterpret_cast<float*>(tail_smem);                       // [7][C]
+  __half* x_h = reinterpret_cast<__half*>(tail_smem + 7 * C * 4);         // [TAIL_TILE + 6][pitch]
+  __half* x_l = x_h + (size_t)(TAIL_TILE + 6) * pitch;                    // THREE only
   const int b = blockIdx.y;
   const long t0 = (long)blockIdx.x * TAIL_TILE;
   const size_t rows = (size_t)p.L + 6;
   const int nrows = (int)min((long)TAIL_TILE + 6, (long)rows - t0);
-  for (int i = threadIdx.x; i < 7 * C; i += TAIL_TILE) w_s[i] = __ldg(p.w + i);
   const int cg = C / 8;
-  for (int idx = threadIdx.x; idx < nrows * cg; idx += TAIL_TILE) {
+  for (int idx = threadIdx.x; idx < (TAIL_TILE + 6) * cg; idx += TAIL_THREADS) {
     const int rr = idx / cg, g = idx - rr * cg;
-    const size_t off = ((size_t)b * rows + t0 + rr) * C + g * 8;
-    const uint4 hq = __ldg(reinterpret_cast<const uint4*>(p.in.hi + off));
-    const __half* h = reinterpret_cast<const __half*>(&hq);
-    float a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = __half2float(h[i]);
-    if (p.terms == 3) {
-      const uint4 lq = __ldg(reinterpret_cast<const uint4*>(p.in.lo + off));
-      const __half* l = reinterpret_cast<const __half*>(&lq);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] += __half2float(l[i]);
+    if (rr < nrows) {
+      const size_t off = ((size_t)b * rows + t0 + rr) * C + g * 8;
+      cp_async16(x_h + rr * pitch + g * 8, p.in.hi + off);
+      if (THREE) cp_async16(x_l + rr * pitch + g * 8, p.in.lo + off);
+    } else {                                                              // rows past the clip: never read as valid
+      *reinterpret_cast<uint4*>(x_h + rr * pitch + g * 8) = make_uint4(0, 0, 0, 0);
+      if (THREE) *reinterpret_cast<uint4*>(x_l + rr * pitch + g * 8) = make_uint4(0, 0, 0, 0);
     }
-    float4* dst = reinterpret_cast<float4*>(x_s + rr * pitch + g * 8);
-    dst[0] = make_float4(a[0], a[1], a[2], a[3]);
-    dst[1] = make_float4(a[4], a[5], a[6], a[7]);
   }
+  for (int i = threadIdx.x; i < 7 * C; i += TAIL_THREADS) w_s[i] = __ldg(p.w + i);
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  const long t = t0 + threadIdx.x;
-  float mag = 0.f;
-  if (t < p.L) {
-    float acc0 = p.bias, acc1 = 0.f;
-    for (int k = 0; k < 7; ++k) {
-      const float4* xr = reinterpret_cast<const float4*>(x_s + (threadIdx.x + k) * pitch);
-      const float4* wr = reinterpret_cast<const float4*>(w_s + k * C);
-#pragma unroll 4
-      for (int c = 0; c < C / 4; c += 2) {
-        const float4 x0 = xr[c], x1 = xr[c + 1], w0 = wr[c], w1 = wr[c + 1];
-        acc0 = fmaf(x0.x, w0.x, acc0); acc0 = fmaf(x0.y, w0.y, acc0); acc0 = fmaf(x0.z, w0.z, acc0); acc0 = fmaf(x0.w, w0.w, acc0);
-        acc1 = fmaf(x1.x, w1.x, acc1); acc1 = fmaf(x1.y, w1.y, acc1); acc1 = fmaf(x1.z, w1.z, acc1); acc1 = fmaf(x1.w, w1.w, acc1);
+
+  float acc[TAIL_RT];
+#pragma unroll
+  for (int o = 0; o < TAIL_RT; ++o) acc[o] = 0.f;
+  const int r0 = threadIdx.x * TAIL_RT;
+  for (int c8 = 0; c8 < cg; ++c8) {
+    float a[TAIL_RT + 6][8];
+#pragma unroll
+    for (int rr = 0; rr < TAIL_RT + 6; ++rr) {
+      const uint4 hq = *reinterpret_cast<const uint4*>(x_h + (r0 + rr) * pitch + c8 * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&hq);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        a[rr][2 * j] = f.x; a[rr][2 * j + 1] = f.y;
+      }
+      if (THREE) {
+        const uint4 lq = *reinterpret_cast<const uint4*>(x_l + (r0 + rr) * pitch + c8 * 8);
+        const __half2* l2 = reinterpret_cast<const __half2*>(&lq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(l2[j]);
+          a[rr][2 * j] += f.x; a[rr][2 * j + 1] += f.y;
+        }
       }
     }
-    const float y = tanhf(acc0 + acc1);
-    p.wav[(size_t)b * p.L + t] = y;
-    mag = fabsf(y);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * C + c8 * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * C + c8 * 8 + 4);
+#pragma unroll
+      for (int o = 0; o < TAIL_RT; ++o) {
+        float s = acc[o];
+        s = fmaf(a[o + k][0], w0.x, s); s = fmaf(a[o + k][1], w0.y, s); s = fmaf(a[o + k][2], w0.z, s); s = fmaf(a[o + k][3], w0.w, s);
+        s = fmaf(a[o + k][4], w1.x, s); s = fmaf(a[o + k][5], w1.y, s); s = fmaf(a[o + k][6], w1.z, s); s = fmaf(a[o + k][7], w1.w, s);
+        acc[o] = s;
+      }
+    }
+  }
+  float mag = 0.f;
+#pragma unroll
+  for (int o = 0; o < TAIL_RT; ++o) {
+    const long t = t0 + r0 + o;
+    if (t < p.L) {
+      const float y = tanhf(acc[o] + p.bias);
+      p.wav[(size_t)b * p.L + t] = y;
+      mag = fmaxf(mag, fabsf(y));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, o));
-  __shared__ float wmax[TAIL_TILE / 32];
+  __shared__ float wmax[TAIL_THREADS / 32];
   if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mag;
   __syncthreads();
   if (threadIdx.x == 0) {
     float m = 0.f;
-    for (int i = 0; i < TAIL_TILE / 32; ++i) m = fmaxf(m, wmax[i]);
+    for (int i = 0; i < TAIL_THREADS / 32; ++i) m = fmaxf(m, wmax[i]);
     atomicMax(p.peak_bits + b, __float_as_uint(m));
   }
 }
 cudaError_t launch_voc_tail(const VocTailParams& p, cudaStream_t stream) {
   dim3 grid((unsigned)((p.L + TAIL_TILE - 1) / TAIL_TILE), p.batch);
-  const size_t smem = (size_t)(7 * p.C + (TAIL_TILE + 6) * (p.C + 4)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(voc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  voc_tail_kernel<<<grid, TAIL_TILE, smem, stream>>>(p);
+  const bool three = p.terms == 3;
+  const size_t smem = (size_t)7 * p.C * 4 + (size_t)(three ? 2 : 1) * (TAIL_TILE + 6) * (p.C + 8) * 2;
+  cudaError_t e = three ? cudaFuncSetAttribute(voc_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                        : cudaFuncSetAttribute(voc_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  if (three) voc_tail_kernel<true><<<grid, TAIL_THREADS, smem, stream>>>(p);
+  else voc_tail_kernel<false><<<grid, TAIL_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
