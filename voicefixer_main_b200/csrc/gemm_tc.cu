@@ -268,6 +268,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
     const int f_row = lane >> 3, f_c16 = lane & 7;       // fp32: 4 rows x 128 B per instruction
     const int h_row = lane >> 2, h_c16 = lane & 3;       // fp16: 8 rows x 64 B per instruction
     const int nseg = (tile_chunks + seg_chunks - 1) / seg_chunks;
+    // staging slots: own row (so_*) and row-major role (sr_*); the swizzle terms are lane constants
+    const int so_h0 = lane * 4, so_hx = (lane >> 1) & 3;            // sw64(lane, i)      = so_h0 + (i ^ so_hx)
+    const int sr_h0 = h_row * 4, sr_hx = h_c16;                     // sw64(8i+h_row, c)  = 32 i + sr_h0 + (c ^ ((h_row >> 1) & 3)) (8i keeps bits 1-2)
+    const int so_f0 = lane * 8, so_fx = lane & 7;                   // sw128(lane, i)     = so_f0 + (i ^ so_fx)
+    const int sr_f0 = f_row * 8;                                    // sw128(4i+f_row, c) = 32 i + sr_f0 + (c ^ ((4i + f_row) & 7))
+#define SO_H(i) (so_h0 + ((i) ^ so_hx))
+#define SR_H(i) (32 * (i) + sr_h0 + (sr_hx ^ ((h_row >> 1) & 3)))
+#define SO_F(i) (so_f0 + ((i) ^ so_fx))
+#define SR_F(i) (32 * (i) + sr_f0 + (f_c16 ^ ((4 * (i) + f_row) & 7)))
+    const bool plain = map == MAP_PLAIN;
     int prev_n0 = -1, ti = 0, g = 0;
     float amax = 0.f;
     bool ok = true;
@@ -294,6 +304,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
       float head_acc = 0.f;
       int cth = 0, ctw = 0;
       uint32_t orow = 0, flags = 0;
+      // Fast path (MAP_PLAIN, i.e. everything but the transposed convs): the rows this lane stores / loads in the
+      // row-major phases are the same for every column chunk, so their element offsets (in 16-byte units) are
+      // computed once per tile; a chunk only adds its column offset.
+      uint32_t ia[4], ir[4], iraw[8], ires[8];
+      uint32_t vh = 0, vf = 0;            // valid-row bit masks for the fp16 (4 rows) and fp32 (8 rows) phases
       if (map == MAP_PLAIN) {             // row mapping independent of the column chunk
         if (row_ok) {
           orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + r);
@@ -302,6 +317,23 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
         __syncwarp();
         rows[lane] = RowInfo{orow, flags};
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const RowInfo ri = rows[8 * i + h_row];
+          vh |= (ri.flags & kRowValid) ? (1u << i) : 0u;
+          ia[i] = (uint32_t)(((size_t)ri.orow * e.out_a.ld + e.out_a.c_off + n0) >> 3) + h_c16;
+          ir[i] = (uint32_t)(((size_t)ri.orow * e.out_r.ld + e.out_r.c_off + n0) >> 3) + h_c16;
+        }
+        if (THREE && (want_raw || has_resid)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + f_row;
+            const RowInfo ri = rows[rr];
+            vf |= (ri.flags & kRowValid) ? (1u << i) : 0u;
+            iraw[i] = (uint32_t)(((size_t)ri.orow * e.raw_ld + n0) >> 2) + f_c16;
+            ires[i] = (uint32_t)((((size_t)img * rows_in + m0 + q * 32 + rr) * e.resid_ld + n0) >> 2) + f_c16;
+          }
+        }
       } else if (map == MAP_CONVT2D) {
         cth = r / Wp;
         ctw = r - cth * Wp;
@@ -339,21 +371,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
             v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
           }
         }
-        if (has_resid) {                  // coalesced global -> staging -> own row
-          const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
+        if (THREE && has_resid) {         // coalesced global -> staging -> own row (MAP_PLAIN only; fp32 streams exist in 3-term mode only)
+          const float4* rp = reinterpret_cast<const float4*>(e.resid) + j * 8;
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + f_row;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + q * 32 + rr < rows_in)
-              x = __ldg(reinterpret_cast<const float4*>(e.resid + rbase + (size_t)rr * e.resid_ld) + f_c16);
-            stg_f[sw128(rr, f_c16)] = x;
+            if ((vf >> i) & 1u) x = __ldg(rp + ires[i]);
+            stg_f[SR_F(i)] = x;
           }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 x = stg_f[sw128(lane, i)];
+            const float4 x = stg_f[SO_F(i)];
             v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
           }
         }
@@ -368,13 +398,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
               xh = __ldg(reinterpret_cast<const uint4*>(e.resid_hi + rbase + (size_t)rr * e.resid_ld) + h_c16);
               xl = __ldg(reinterpret_cast<const uint4*>(e.resid_lo + rbase + (size_t)rr * e.resid_ld) + h_c16);
             }
-            stg_h[sw64(rr, h_c16)] = xh;
-            stg_l[sw64(rr, h_c16)] = xl;
+            stg_h[SR_H(i)] = xh;
+            stg_l[SR_H(i)] = xl;
           }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 xh = stg_h[sw64(lane, i)], xl = stg_l[sw64(lane, i)];
+            const uint4 xh = stg_h[SO_H(i)], xl = stg_l[SO_H(i)];
             const __half2* ph = reinterpret_cast<const __half2*>(&xh);
             const __half2* pl = reinterpret_cast<const __half2*>(&xl);
 #pragma unroll
@@ -390,17 +420,24 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (want_raw) {                   // fp32 output
+        if (THREE && want_raw) {          // fp32 output
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) stg_f[sw128(lane, i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) stg_f[SO_F(i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           __syncwarp();
+          if (plain) {
+            float4* op = reinterpret_cast<float4*>(e.out_raw) + j * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + f_row;
-            const RowInfo ri = rows[rr];
-            if (ri.flags & kRowValid)
-              reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[sw128(rr, f_c16)];
+            for (int i = 0; i < 8; ++i)
+              if ((vf >> i) & 1u) op[iraw[i]] = stg_f[SR_F(i)];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + f_row;
+              const RowInfo ri = rows[rr];
+              if (ri.flags & kRowValid)
+                reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[SR_F(i)];
+            }
           }
         }
         if (want_r) {                     // raw hi/lo planes
@@ -409,18 +446,26 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            stg_h[sw64(lane, i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            stg_l[sw64(lane, i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            stg_h[SO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
+          if (plain) {
+            uint4* ph = reinterpret_cast<uint4*>(e.out_r.hi) + j * 4;
+            uint4* pl = reinterpret_cast<uint4*>(e.out_r.lo) + j * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + h_row;
-            const RowInfo ri = rows[rr];
-            if (ri.flags & kRowValid) {
-              const size_t o = (size_t)ri.orow * e.out_r.ld + e.out_r.c_off + co0;
-              reinterpret_cast<uint4*>(e.out_r.hi + o)[h_c16] = stg_h[sw64(rr, h_c16)];
-              reinterpret_cast<uint4*>(e.out_r.lo + o)[h_c16] = stg_l[sw64(rr, h_c16)];
+            for (int i = 0; i < 4; ++i)
+              if ((vh >> i) & 1u) { ph[ir[i]] = stg_h[SR_H(i)]; pl[ir[i]] = stg_l[SR_H(i)]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + h_row;
+              const RowInfo ri = rows[rr];
+              if (ri.flags & kRowValid) {
+                const size_t o = (size_t)ri.orow * e.out_r.ld + e.out_r.c_off + co0;
+                reinterpret_cast<uint4*>(e.out_r.hi + o)[h_c16] = stg_h[SR_H(i)];
+                reinterpret_cast<uint4*>(e.out_r.lo + o)[h_c16] = stg_l[SR_H(i)];
+              }
             }
           }
         }
@@ -459,18 +504,29 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            stg_h[sw64(lane, i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            if (THREE) stg_l[sw64(lane, i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            stg_h[SO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            if (THREE) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
+          if (plain) {
+            uint4* ph = reinterpret_cast<uint4*>(e.out_a.hi) + j * 4;
+            uint4* pl = reinterpret_cast<uint4*>(e.out_a.lo) + j * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + h_row;
-            const RowInfo ri = rows[rr];
-            if (ri.flags & kRowValid) {
-              const size_t o = (size_t)ri.orow * e.out_a.ld + e.out_a.c_off + co0;
-              reinterpret_cast<uint4*>(e.out_a.hi + o)[h_c16] = stg_h[sw64(rr, h_c16)];
-              if (THREE) reinterpret_cast<uint4*>(e.out_a.lo + o)[h_c16] = stg_l[sw64(rr, h_c16)];
+            for (int i = 0; i < 4; ++i)
+              if ((vh >> i) & 1u) {
+                ph[ia[i]] = stg_h[SR_H(i)];
+                if (THREE) pl[ia[i]] = stg_l[SR_H(i)];
+              }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + h_row;
+              const RowInfo ri = rows[rr];
+              if (ri.flags & kRowValid) {
+                const size_t o = (size_t)ri.orow * e.out_a.ld + e.out_a.c_off + co0;
+                reinterpret_cast<uint4*>(e.out_a.hi + o)[h_c16] = stg_h[SR_H(i)];
+                if (THREE) reinterpret_cast<uint4*>(e.out_a.lo + o)[h_c16] = stg_l[SR_H(i)];
+              }
             }
           }
         }
