@@ -1463,6 +1463,8 @@ VF_API int vf_selftest_gemm(vf_ctx* ctx, int n_img, int rows, int cin, int cout,
   }
   Planes A = b.planes(n_img, rows, cin);
   float* out[2] = {b.alloc<float>((size_t)n_img * rows * cout), b.alloc<float>((size_t)n_img * rows * cout)};
+  // hi-only kernels carry no fp32 stream: their result is observed through the raw hi/lo planes (22 bits)
+  Planes outp[2] = {b.planes(n_img, rows, cout), b.planes(n_img, rows, cout)};
   if (b.rc) return b.rc;
   CK(cudaMemcpy(A.p.hi, ahi.data(), an * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(A.p.lo, alo.data(), an * 2, cudaMemcpyHostToDevice));
@@ -1472,8 +1474,12 @@ VF_API int vf_selftest_gemm(vf_ctx* ctx, int n_img, int rows, int cin, int cout,
     std::vector<Op> ops;
     GemmEpilogue e = epi_plain(rows, 0, cout, rows);
     e.bias = W.bias;
-    e.out_raw = out[impl];
-    e.raw_ld = cout;
+    if (terms == 3) {
+      e.out_raw = out[impl];
+      e.raw_ld = cout;
+    } else {
+      e.out_r = OutPlane{outp[impl].p.hi, outp[impl].p.lo, cout, 0};
+    }
     std::vector<GemmTap> taps;
     for (int t = 0; t < ntaps; ++t) taps.push_back(GemmTap{(t - (ntaps - 1) / 2) * dilation, 0, 0, 0, cin});
     b.gemm(ops, W, ASrc{A, rows, 0}, nullptr, taps, e, n_img, terms);
@@ -1486,8 +1492,18 @@ VF_API int vf_selftest_gemm(vf_ctx* ctx, int n_img, int rows, int cin, int cout,
   if (!rc && se == cudaSuccess) {
     const size_t on = (size_t)n_img * rows * cout;
     std::vector<float> h0(on), h1(on);
-    cudaMemcpy(h0.data(), out[0], on * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(h1.data(), out[1], on * 4, cudaMemcpyDeviceToHost);
+    if (terms == 3) {
+      cudaMemcpy(h0.data(), out[0], on * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h1.data(), out[1], on * 4, cudaMemcpyDeviceToHost);
+    } else {
+      std::vector<__half> ph(on), pl(on);
+      for (int impl = 0; impl < 2; ++impl) {
+        cudaMemcpy(ph.data(), outp[impl].p.hi, on * 2, cudaMemcpyDeviceToHost);
+        cudaMemcpy(pl.data(), outp[impl].p.lo, on * 2, cudaMemcpyDeviceToHost);
+        std::vector<float>& h = impl ? h1 : h0;
+        for (size_t i = 0; i < on; ++i) h[i] = __half2float(ph[i]) + __half2float(pl[i]);
+      }
+    }
     for (size_t i = 0; i < on; ++i) {
       const double d = std::fabs((double)h0[i] - (double)h1[i]);
       if (!(d <= md)) md = d;          // NaN-propagating max

@@ -34,10 +34,8 @@ struct RowInfo {        // published per epilogue thread for its own row, read b
   uint32_t flags;
 };
 
-// 32 rows x 128 B staging tile (fp32 x 32 columns): 16-byte column index is XOR-swizzled with the row.
-__device__ __forceinline__ int sw128(int row, int c16) { return row * 8 + (c16 ^ (row & 7)); }
-// 32 rows x 64 B staging tile (fp16 x 32 columns)
-__device__ __forceinline__ int sw64(int row, int c16) { return row * 4 + (c16 ^ ((row >> 1) & 3)); }
+// Staging tiles: 32 rows x 128 B (fp32 x 32 columns), 16-byte column index XOR (row & 7); and 32 rows x 64 B
+// (fp16 x 32 columns), 16-byte column index XOR ((row >> 1) & 3).  See the SO_* / SR_* macros in the epilogue.
 
 __device__ __forceinline__ void epi_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
@@ -277,7 +275,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
 #define SR_H(i) (32 * (i) + sr_h0 + (sr_hx ^ ((h_row >> 1) & 3)))
 #define SO_F(i) (so_f0 + ((i) ^ so_fx))
 #define SR_F(i) (32 * (i) + sr_f0 + (f_c16 ^ ((4 * (i) + f_row) & 7)))
-    const bool plain = map == MAP_PLAIN;
+    const bool plain = !THREE && map == MAP_PLAIN;   // per-tile precomputed store indices (hi-only kernels)
     int prev_n0 = -1, ti = 0, g = 0;
     float amax = 0.f;
     bool ok = true;
@@ -307,8 +305,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
       // Fast path (MAP_PLAIN, i.e. everything but the transposed convs): the rows this lane stores / loads in the
       // row-major phases are the same for every column chunk, so their element offsets (in 16-byte units) are
       // computed once per tile; a chunk only adds its column offset.
-      uint32_t ia[4], ir[4], iraw[8], ires[8];
-      uint32_t vh = 0, vf = 0;            // valid-row bit masks for the fp16 (4 rows) and fp32 (8 rows) phases
+      uint32_t ia[4], ir[4];              // hi-only kernels only (3-term kernels need the registers for promotion)
+      uint32_t vh = 0;                    // valid-row bit mask of the 4 rows this lane stores
       if (map == MAP_PLAIN) {             // row mapping independent of the column chunk
         if (row_ok) {
           orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + r);
@@ -317,21 +315,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
         __syncwarp();
         rows[lane] = RowInfo{orow, flags};
         __syncwarp();
+        if (!THREE) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const RowInfo ri = rows[8 * i + h_row];
-          vh |= (ri.flags & kRowValid) ? (1u << i) : 0u;
-          ia[i] = (uint32_t)(((size_t)ri.orow * e.out_a.ld + e.out_a.c_off + n0) >> 3) + h_c16;
-          ir[i] = (uint32_t)(((size_t)ri.orow * e.out_r.ld + e.out_r.c_off + n0) >> 3) + h_c16;
-        }
-        if (THREE && (want_raw || has_resid)) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + f_row;
-            const RowInfo ri = rows[rr];
-            vf |= (ri.flags & kRowValid) ? (1u << i) : 0u;
-            iraw[i] = (uint32_t)(((size_t)ri.orow * e.raw_ld + n0) >> 2) + f_c16;
-            ires[i] = (uint32_t)((((size_t)img * rows_in + m0 + q * 32 + rr) * e.resid_ld + n0) >> 2) + f_c16;
+          for (int i = 0; i < 4; ++i) {
+            const RowInfo ri = rows[8 * i + h_row];
+            vh |= (ri.flags & kRowValid) ? (1u << i) : 0u;
+            ia[i] = (uint32_t)(((size_t)ri.orow * e.out_a.ld + e.out_a.c_off + n0) >> 3) + h_c16;
+            ir[i] = (uint32_t)(((size_t)ri.orow * e.out_r.ld + e.out_r.c_off + n0) >> 3) + h_c16;
           }
         }
       } else if (map == MAP_CONVT2D) {
@@ -372,12 +362,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
           }
         }
         if (THREE && has_resid) {         // coalesced global -> staging -> own row (MAP_PLAIN only; fp32 streams exist in 3-term mode only)
-          const float4* rp = reinterpret_cast<const float4*>(e.resid) + j * 8;
+          const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + f_row;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((vf >> i) & 1u) x = __ldg(rp + ires[i]);
+            if (m0 + q * 32 + rr < rows_in)
+              x = __ldg(reinterpret_cast<const float4*>(e.resid + rbase + (size_t)rr * e.resid_ld) + f_c16);
             stg_f[SR_F(i)] = x;
           }
           __syncwarp();
@@ -425,19 +417,12 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
 #pragma unroll
           for (int i = 0; i < 8; ++i) stg_f[SO_F(i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           __syncwarp();
-          if (plain) {
-            float4* op = reinterpret_cast<float4*>(e.out_raw) + j * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((vf >> i) & 1u) op[iraw[i]] = stg_f[SR_F(i)];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + f_row;
-              const RowInfo ri = rows[rr];
-              if (ri.flags & kRowValid)
-                reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[SR_F(i)];
-            }
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + f_row;
+            const RowInfo ri = rows[rr];
+            if (ri.flags & kRowValid)
+              reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[SR_F(i)];
           }
         }
         if (want_r) {                     // raw hi/lo planes
