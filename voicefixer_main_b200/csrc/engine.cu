@@ -526,7 +526,9 @@ struct Builder {
     if (bk == 64 && !promoted) {
       int ksum = 0;
       for (auto& t : taps) ksum += t.nch;
-      if (ksum <= 256) bk = 32;
+      int maxk = 256;
+      if (const char* ov = getenv("VF_TUNE_BK32_MAXK")) maxk = atoi(ov);
+      if (ksum <= maxk) bk = 32;
     }
     const int N = W.N;
     // 1-term (hi-only) GEMMs stream half the operand bytes per MMA, so they are L2-bandwidth bound at 128-wide
