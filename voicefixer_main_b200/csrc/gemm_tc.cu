@@ -134,35 +134,40 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // The two issue warps run their loops warp-uniformly (all 32 lanes poll the barriers and keep the counters);
+  // only the instructions that must come from one thread sit under elect.sync.  Running the whole loop under
+  // `if (lane == 0)` makes the compiler wrap every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop, which
+  // measured ~1300 cycles per K chunk on the issue path (ncu, voc.res3.1.a) - the bottleneck of small-chunk layers.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;              // ring slot and its phase bit advance by increment: no division on the issue path
-      uint32_t ph = 0;
-      bool ok = true;
-      if (w_res) {            // weight-stationary: the single N tile's weights, chunk by chunk in MMA order
-        mbar_expect_tx(w_full_bar, (uint32_t)P.w_bytes);
-        uint8_t* wp = w_base;
-        for (int t = 0; t < pr.ntaps; ++t) {
-          const GemmTap tap = pr.taps[t];
-          for (int c = 0; c < tap.nch; c += BK)
-            for (int gi = 0; gi < tap.g; ++gi, wp += B_SLOT) {
-              tma_load_2d(wp, &P.b_hi, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
-              if (THREE) tma_load_2d(wp + B_BYTES, &P.b_lo, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
-            }
-        }
+    int s = 0;              // ring slot and its phase bit advance by increment: no division on the issue path
+    uint32_t ph = 0;
+    bool ok = true;
+    if (w_res && elect_one()) {   // weight-stationary: the single N tile's weights, chunk by chunk in MMA order
+      mbar_expect_tx(w_full_bar, (uint32_t)P.w_bytes);
+      uint8_t* wp = w_base;
+      for (int t = 0; t < pr.ntaps; ++t) {
+        const GemmTap tap = pr.taps[t];
+        for (int c = 0; c < tap.nch; c += BK)
+          for (int gi = 0; gi < tap.g; ++gi, wp += B_SLOT) {
+            tma_load_2d(wp, &P.b_hi, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
+            if (THREE) tma_load_2d(wp + B_BYTES, &P.b_lo, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
+          }
       }
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int nt = tile % n_tiles, mt = tile / n_tiles;
-        const int img = mt / pr.m_tiles;
-        const int m0 = (mt - img * pr.m_tiles) * GEMM_BM;
-        const int n0 = nt * BN;
-        for (int t = 0; t < pr.ntaps && ok; ++t) {
-          const GemmTap tap = pr.taps[t];
-          const bool a_lo = THREE || tap.both;
-          const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + (w_res ? 0 : tap.g * B_SLOT);
-          for (int c = 0; c < tap.nch; c += BK) {
-            if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+    }
+    __syncwarp();
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      const int nt = tile % n_tiles, mt = tile / n_tiles;
+      const int img = mt / pr.m_tiles;
+      const int m0 = (mt - img * pr.m_tiles) * GEMM_BM;
+      const int n0 = nt * BN;
+      for (int t = 0; t < pr.ntaps && ok; ++t) {
+        const GemmTap tap = pr.taps[t];
+        const bool a_lo = THREE || tap.both;
+        const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + (w_res ? 0 : tap.g * B_SLOT);
+        for (int c = 0; c < tap.nch; c += BK) {
+          if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+          if (elect_one()) {
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(full_bar + s, tx);
             tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
@@ -172,59 +177,60 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
               tma_load_2d(sb, &P.b_hi, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
               if (THREE) tma_load_2d(sb + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
             }
-            if (++s == stages) { s = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
-      constexpr uint32_t idesc2 = make_idesc_f16(GEMM_BM, THREE ? 2 * BN : BN);   // hi x [hi | lo]
-      constexpr int ACC_W = THREE ? 2 * BN : BN;
-      int s = 0, ti = 0, g = 0;       // smem ring slot, tile counter, accumulation-segment counter
-      uint32_t ph = 0;                // phase bit of the ring slot
-      bool ok = true;
-      if (w_res) {
-        ok = mbar_wait(w_full_bar, 0, e.err, ERR_PIPE_MMA);
-        tc_fence_after();
-      }
-      const uint32_t w_addr = smem_u32(w_base);
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
-        uint32_t d_main = 0, m_started = 0;
-        uint32_t w_cur = w_addr;      // resident weights are consumed in the order they were loaded
-        int left_in_tile = tile_chunks, left_in_seg = 0, buf = 0;   // countdowns: no division on the issue path
-        for (int t = 0; t < pr.ntaps && ok; ++t) {
-          const int nch = pr.taps[t].nch;
-          const bool both = pr.taps[t].both != 0;
-          const int tg = pr.taps[t].g;
-          const int sh0 = pr.taps[t].shift[0], sh1 = pr.taps[t].shift[1], sh2 = pr.taps[t].shift[2];
-          for (int c = 0; c < nch; c += BK) {
-            if (left_in_seg == 0) {              // open a segment: its accumulator buffer must have been drained
-              left_in_seg = min(seg_chunks, left_in_tile);
-              buf = g & 1;
-              if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
-              tc_fence_after();
-              d_main = tmem_base + buf * ACC_W;
-              m_started = 0;
-            }
-            if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
-            tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+    constexpr uint32_t idesc2 = make_idesc_f16(GEMM_BM, THREE ? 2 * BN : BN);   // hi x [hi | lo]
+    constexpr int ACC_W = THREE ? 2 * BN : BN;
+    int s = 0, ti = 0, g = 0;       // smem ring slot, tile counter, accumulation-segment counter
+    uint32_t ph = 0;                // phase bit of the ring slot
+    bool ok = true;
+    if (w_res) {
+      ok = mbar_wait(w_full_bar, 0, e.err, ERR_PIPE_MMA);
+      tc_fence_after();
+    }
+    const uint32_t w_addr = smem_u32(w_base);
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
+      uint32_t d_main = 0, m_started = 0;
+      uint32_t w_cur = w_addr;      // resident weights are consumed in the order they were loaded
+      int left_in_tile = tile_chunks, left_in_seg = 0, buf = 0;   // countdowns: no division on the issue path
+      for (int t = 0; t < pr.ntaps && ok; ++t) {
+        const int nch = pr.taps[t].nch;
+        const bool both = pr.taps[t].both != 0;
+        const int tg = pr.taps[t].g;
+        const int sh0 = pr.taps[t].shift[0], sh1 = pr.taps[t].shift[1], sh2 = pr.taps[t].shift[2];
+        for (int c = 0; c < nch; c += BK) {
+          if (left_in_seg == 0) {              // open a segment: its accumulator buffer must have been drained
+            left_in_seg = min(seg_chunks, left_in_tile);
+            buf = g & 1;
+            if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+            d_main = tmem_base + buf * ACC_W;
+            m_started = 0;
+          }
+          if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+          tc_fence_after();
+          --left_in_tile;
+          const bool close_seg = --left_in_seg == 0;
+          if (elect_one()) {
             const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t a_lo = a_hi + a_slot;
             // descriptors differ only in the 14-bit start-address field (units of 16 B): +2 per 32-byte K step,
             // +ROW_BYTES/16 per row of halo shift
             const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), da_lo0 = make_smem_desc(a_lo, ROW_BYTES);
+            uint32_t started = m_started;
             for (int gi = 0; gi < tg; ++gi) {
               const int sh = (gi == 0 ? sh0 : (gi == 1 ? sh1 : sh2)) * (ROW_BYTES / 16);
-              const uint64_t db0 = make_smem_desc(w_res ? w_cur : a_hi + off_b + gi * B_SLOT, ROW_BYTES);   // spans [B_hi; B_lo]
-              w_cur += B_SLOT;
+              const uint64_t db0 = make_smem_desc(w_res ? w_cur + gi * B_SLOT : a_hi + off_b + gi * B_SLOT, ROW_BYTES);   // spans [B_hi; B_lo]
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                umma_f16(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, idesc2, m_started);
-                m_started = 1;
+                umma_f16(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, idesc2, started);
+                started = 1;
                 if (THREE) {
                   umma_f16(d_main + BN, da_lo0 + sh + 2 * k, db0 + 2 * k, idesc, 1u);
                 } else if (both) {
@@ -232,18 +238,17 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
                 }
               }
             }
-            umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
-            if (++s == stages) { s = 0; ph ^= 1; }
-            --left_in_tile;
-            if (--left_in_seg == 0) {            // close the segment
-              umma_commit(seg_full_bar + buf);
-              ++g;
-            }
+            umma_commit(empty_bar + s);              // frees the smem slot once these MMAs have read it
+            if (close_seg) umma_commit(seg_full_bar + buf);
           }
+          __syncwarp();
+          m_started = 1;
+          w_cur += tg * B_SLOT;
+          if (close_seg) ++g;
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
     const int ew = warp - 2;
