@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
         const bool a_lo = THREE || tap.both;
         const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + (w_res ? 0 : tap.g * B_SLOT);
         for (int c = 0; c < tap.nch; c += BK) {
-          if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+          if (!mbar_wait_warp(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
           if (elect_one()) {
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(full_bar + s, tx);
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
     uint32_t ph = 0;                // phase bit of the ring slot
     bool ok = true;
     if (w_res) {
-      ok = mbar_wait(w_full_bar, 0, e.err, ERR_PIPE_MMA);
+      ok = mbar_wait_warp(w_full_bar, 0, e.err, ERR_PIPE_MMA);
       tc_fence_after();
     }
     const uint32_t w_addr = smem_u32(w_base);
@@ -209,11 +209,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
           if (left_in_seg == 0) {              // open a segment: its accumulator buffer must have been drained
             left_in_seg = min(seg_chunks, left_in_tile);
             buf = g & 1;
-            if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+            if (!mbar_wait_warp(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
             d_main = tmem_base + buf * ACC_W;
             m_started = 0;
           }
-          if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+          if (!mbar_wait_warp(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
           tc_fence_after();
           --left_in_tile;
           const bool close_seg = --left_in_seg == 0;
