@@ -134,16 +134,18 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  // The two issue warps run their loops warp-uniformly (all 32 lanes poll the barriers and keep the counters);
-  // only the instructions that must come from one thread sit under elect.sync.  Running the whole loop under
-  // `if (lane == 0)` makes the compiler wrap every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop, which
-  // measured ~1300 cycles per K chunk on the issue path (ncu, voc.res3.1.a) - the bottleneck of small-chunk layers.
+  // Each issue warp elects ONE thread (elect.sync) that runs the whole loop.  Running it under `if (lane == 0)`
+  // instead makes the compiler wrap every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop (it cannot prove a
+  // single active thread), which measured ~1300 cycles per K chunk on the issue path (ncu, voc.res3.1.a) - the
+  // bottleneck of small-chunk layers.  Measured alternatives: all 32 lanes polling (small-chunk layers -17 %, but
+  // MMA-bound layers +8 %), lane-0 polling with a shuffle broadcast (+12 % overall).
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {      // ONE elected thread runs the whole loop (see above)
     int s = 0;              // ring slot and its phase bit advance by increment: no division on the issue path
     uint32_t ph = 0;
     bool ok = true;
-    if (w_res && elect_one()) {   // weight-stationary: the single N tile's weights, chunk by chunk in MMA order
+    if (w_res) {            // weight-stationary: the single N tile's weights, chunk by chunk in MMA order
       mbar_expect_tx(w_full_bar, (uint32_t)P.w_bytes);
       uint8_t* wp = w_base;
       for (int t = 0; t < pr.ntaps; ++t) {
@@ -155,7 +157,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
           }
       }
     }
-    __syncwarp();
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       const int nt = tile % n_tiles, mt = tile / n_tiles;
       const int img = mt / pr.m_tiles;
@@ -166,8 +167,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
         const bool a_lo = THREE || tap.both;
         const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + (w_res ? 0 : tap.g * B_SLOT);
         for (int c = 0; c < tap.nch; c += BK) {
-          if (!mbar_wait_warp(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
-          if (elect_one()) {
+          if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+          {
             uint8_t* st = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(full_bar + s, tx);
             tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
@@ -178,13 +179,15 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
               if (THREE) tma_load_2d(sb + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
             }
           }
-          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
     constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
     constexpr uint32_t idesc2 = make_idesc_f16(GEMM_BM, THREE ? 2 * BN : BN);   // hi x [hi | lo]
     constexpr int ACC_W = THREE ? 2 * BN : BN;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
     uint32_t ph = 0;                // phase bit of the ring slot
     bool ok = true;
     if (w_res) {
-      ok = mbar_wait_warp(w_full_bar, 0, e.err, ERR_PIPE_MMA);
+      ok = mbar_wait(w_full_bar, 0, e.err, ERR_PIPE_MMA);
       tc_fence_after();
     }
     const uint32_t w_addr = smem_u32(w_base);
@@ -209,15 +212,15 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
           if (left_in_seg == 0) {              // open a segment: its accumulator buffer must have been drained
             left_in_seg = min(seg_chunks, left_in_tile);
             buf = g & 1;
-            if (!mbar_wait_warp(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+            if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
             d_main = tmem_base + buf * ACC_W;
             m_started = 0;
           }
-          if (!mbar_wait_warp(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+          if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
           tc_fence_after();
           --left_in_tile;
           const bool close_seg = --left_in_seg == 0;
-          if (elect_one()) {
+          {
             const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t a_lo = a_hi + a_slot;
             // descriptors differ only in the 14-bit start-address field (units of 16 B): +2 per 32-byte K step,
@@ -241,7 +244,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
             umma_commit(empty_bar + s);              // frees the smem slot once these MMAs have read it
             if (close_seg) umma_commit(seg_full_bar + buf);
           }
-          __syncwarp();
           m_started = 1;
           w_cur += tg * B_SLOT;
           if (close_seg) ++g;
@@ -249,6 +251,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
         }
       }
     }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
     const int ew = warp - 2;

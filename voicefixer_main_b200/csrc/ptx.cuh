@@ -61,13 +61,6 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
   return false;
 }
 
-// Warp-uniform wait: lane 0 polls (one mbarrier transaction per poll instead of 32), the result is broadcast.
-__device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity, int* err, int code) {
-  int ok = 1;
-  if ((threadIdx.x & 31) == 0) ok = mbar_wait(bar, parity, err, code) ? 1 : 0;
-  return __shfl_sync(0xffffffffu, ok, 0) != 0;
-}
-
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
