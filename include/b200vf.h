@@ -125,7 +125,7 @@ VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n_samples, size_t*
 /* Synchronises `stream`, reads and clears the sticky device flags.  VF_OK, VF_EDEVICE or VF_EASSERT. */
 VF_API int vf_check_errors(vf_ctx* ctx, void* stream);
 
-/* Options: "unet_terms" / "vocoder_terms" (1 or 3 fp16 split terms), "unify_energy" (1: vf_restore applies
+/* Options: "vocoder_terms" (1 or 3 fp16 split terms; "unet_terms" accepts only 3), "unify_energy" (1: vf_restore applies
  * amp_to_original_f, tools/utils.py:50-55, as handler() does when meta["unify_energy"] is set),
  * "validate_simt" (1: run every GEMM on the SIMT validation kernel instead of tcgen05 - tests only). */
 VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value);

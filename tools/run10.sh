@@ -1,0 +1,6 @@
+timeout 700 python -m pytest tests -q -m gpu --tb=short -x 2>&1 | tail -5
+bash tools/run_ab.sh base "VF_X=0" base2 "VF_X=0"
+for spec in voc_res3_1_a:165 voc_res2_1_a:148 enc3_b2_conv1:17; do
+  name=${spec%%:*}; idx=${spec##*:}
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s $((179+idx)) -c 1 -f -o gpurun_out/prof_$name python tools/profile_step.py --steps 2 > gpurun_out/ncu_$name.log 2>&1; tail -1 gpurun_out/ncu_$name.log | cut -c1-200
+done

@@ -26,7 +26,8 @@
 namespace vf {
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
 size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes);
-void gemm_tc_set_bn64_ew4(bool on);
+int gemm_tc_max_ctas(int bn);
+uint32_t gemm_tc_magic(uint32_t d, uint64_t nmax);
 cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
 }  // namespace vf
 
@@ -522,11 +523,12 @@ struct Builder {
       }
       if (main64 && padok && taps.size() > 1) { bk = 64; promoted = true; }
     }
-    // small-K layers are bound by loads/stores, not MMAs: narrower K chunks -> smaller stages -> 2-3 CTAs per SM
+    // K chunk width: every chunk costs the two single-thread issue loops a fixed ~0.5 us round (barrier wait, TMA /
+    // MMA operand set-up), so wide chunks win even where narrow ones would allow one more co-resident CTA
     if (bk == 64 && !promoted) {
       int ksum = 0;
       for (auto& t : taps) ksum += t.nch;
-      int maxk = 256;
+      int maxk = 0;   // measured: halving the chunk count beats the extra co-resident CTA (voc.res3.a 1.43 -> 0.96 ms)
       if (const char* ov = getenv("VF_TUNE_BK32_MAXK")) maxk = atoi(ov);
       if (ksum <= maxk) bk = 32;
     }
@@ -535,6 +537,10 @@ struct Builder {
     // tiles: use 256-wide N tiles where the accumulator budget allows (one accumulator, double buffered)
     const int bn = (terms == 1 && N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : (N % 64 == 0) ? 64 : 32;
     if (N % 32) { rc = fail(ctx, VF_EINVAL, "GEMM N=%d not a multiple of 32", N); return; }
+    if (terms == 1 && (epi.a_scale || epi.head_w || epi.out_raw || epi.resid)) {
+      rc = fail(ctx, VF_EINVAL, "1-term GEMM with an affine / head / fp32 stream epilogue (3-term kernels only)");
+      return;
+    }
     int k = 0;
     for (auto& t : taps) {
       t.k_off = k;
@@ -548,12 +554,18 @@ struct Builder {
     // layer is bound by shared-memory / L2 feed traffic (narrow N); wide-N tiles keep the finer-grained ring.
     int gmax = 1;
     {
-      // measured (B = 32 x 10 s, same box): BN = 64 layers gain 8-17 %, BN = 32 layers lose 3-5 % (their stage grows
-      // past the 3-CTA/SM budget), 3-term BN = 128 stages would not fit twice in shared memory
-      bool want = ctx->validate_simt == 0 && (bn == 64 || (terms == 1 && bn == 128));
-      if (const char* ov = getenv("VF_TUNE_HALO")) want = want && atoi(ov) != 0;
+      // measured (B = 32 x 10 s, same box): BN = 64 layers gain 8-17 %, BN = 32 layers 15-25 % (9x L2->SM re-reads of
+      // the taps become 3x); a grouping whose stage no longer fits twice falls back to single taps
+      bool want = ctx->validate_simt == 0;
+      if (const char* ov = getenv("VF_TUNE_HALO")) {      // 0: never, 1: only BN = 64 and hi-only BN = 128 tiles
+        if (atoi(ov) == 0) want = false;
+        if (atoi(ov) == 1) want = want && (bn == 64 || (terms == 1 && bn == 128));
+      }
       if (want) {
         std::vector<GemmTap> grouped;
+        int gm = 1;
+        bool any_both = false;
+        for (auto& t : taps) any_both |= t.both != 0;
         for (size_t i = 0; i < taps.size();) {
           GemmTap gt = taps[i];
           size_t n = 1;
@@ -570,11 +582,15 @@ struct Builder {
           for (size_t j = 0; j < n; ++j) gt.shift[j] = taps[i + j].a_off - lo;
           gt.a_off = lo;
           gt.g = (int)n;
-          gmax = std::max(gmax, gt.g);
+          gm = std::max(gm, gt.g);
           grouped.push_back(gt);
           i += n;
         }
-        taps.swap(grouped);
+        // a grouped stage holds up to 3 weight tiles: keep the grouping only if a 2-deep ring still fits
+        if (gm > 1 && gemm_tc_smem_bytes(bn, bk, 2, (terms == 3 || any_both) ? 2 : 1, terms, GEMM_BM + 2, gm, 0) <= (size_t)226 * 1024) {
+          taps.swap(grouped);
+          gmax = gm;
+        }
       }
     }
     const int a_box_rows = gmax > 1 ? GEMM_BM + 2 : GEMM_BM;
@@ -629,11 +645,14 @@ struct Builder {
       tp.planes_a = (terms == 3 || any_both) ? 2 : 1;
       auto pow2 = [](int x) { int c = 32; while (c < x) c *= 2; return c; };
       // occupancy: small-K tiles are bound by loads/stores -> several persistent CTAs per SM; large-K -> one
-      const bool ew4 = getenv("VF_TUNE_BN64_EW4") && atoi(getenv("VF_TUNE_BN64_EW4")) != 0;
-      gemm_tc_set_bn64_ew4(ew4);
-      const int reg_limit = bn == 32 ? 3 : (bn == 64 ? ((ew4 && terms == 1) ? 3 : 2) : 1);   // matches __launch_bounds__ in gemm_tc.cu
+      const int reg_limit = gemm_tc_max_ctas(bn);
       int ctas = (k <= 1024) ? reg_limit : 1;
       if (const char* ov = getenv("VF_TUNE_SMALLK_CTAS")) { if (k <= 1024) ctas = std::max(1, std::min(reg_limit, atoi(ov))); }
+      {   // per tile shape: VF_TUNE_CTAS_<bn>_<terms>=n
+        char key[48];
+        snprintf(key, sizeof key, "VF_TUNE_CTAS_%d_%d", bn, terms);
+        if (const char* ov = getenv(key)) { if (k <= 1024) ctas = std::max(1, std::min(reg_limit, atoi(ov))); }
+      }
       int stages = 0;
       // weight-stationary: one N tile, load/store-bound layer, weights + a ring of >= 2 tiles of activations fit
       int n_wslots = 0;
@@ -644,14 +663,16 @@ struct Builder {
       bool w_res = false;
       if (const char* ov = getenv("VF_TUNE_WRES")) w_res = N == bn && k <= 1024 && w_bytes <= 100 * 1024 && (atoi(ov) == 2 || (atoi(ov) == 1 && terms == 1));
       if (w_res) {
-        for (stages = 16; stages >= 2; --stages)
-          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, w_bytes) <= (size_t)226 * 1024) break;
-        if (stages >= std::min(2 * tp.tile_chunks, 6)) {
-          ctas = 1;
-          tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
-        } else {
-          w_res = false;
+        bool found = false;
+        tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
+        for (int c = ctas; c >= 1 && !found; --c) {
+          if (tp.tmem_cols * c > 512) continue;
+          const size_t per_cta = (size_t)227 * 1024 / c - 1024;
+          for (stages = 12; stages >= 3; --stages)
+            if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, w_bytes) <= per_cta) break;
+          if (stages >= 3) { ctas = c; found = true; }
         }
+        if (!found) w_res = false;
       }
       tp.w_resident = w_res ? 1 : 0;
       tp.w_bytes = w_res ? w_bytes : 0;
@@ -665,8 +686,11 @@ struct Builder {
       }
       if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }
       tp.stages = stages;
+      tp.ctas_per_sm = ctas;
       const long total_tiles = (long)n_img * pr.m_tiles * (N / bn);
       tp.grid = (int)std::min<long>(total_tiles, (long)ctx->sm_count * ctas);
+      tp.magic_n = gemm_tc_magic((uint32_t)(N / bn), (uint64_t)total_tiles);
+      tp.magic_m = gemm_tc_magic((uint32_t)pr.m_tiles, (uint64_t)n_img * pr.m_tiles);
       tp.prob = pr;
     }
     {   // algorithmic work: the reference op's own MAC count and the minimum HBM traffic of this launch
@@ -1376,6 +1400,9 @@ VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value) {
   int* slot = nullptr;
   if (k == "unet_terms" || k == "vocoder_terms") {
     if (value != 1 && value != 3) return fail(ctx, VF_EINVAL, "%s must be 1 or 3", key);
+    // the UNet's fp32 skip streams, BN affines and fused head exist in the 3-term kernels only (the 1e-4 log-mel
+    // bar needs fp32-grade products anyway)
+    if (k == "unet_terms" && value != 3) return fail(ctx, VF_EINVAL, "unet_terms: only 3 is supported");
     slot = k == "unet_terms" ? &ctx->unet_terms : &ctx->voc_terms;
   } else if (k == "unify_energy") {
     ctx->unify_energy = value ? 1 : 0;     // per-call behaviour, no plan rebuild needed

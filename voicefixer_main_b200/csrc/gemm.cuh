@@ -109,6 +109,8 @@ struct GemmTcParams {
                    //    ring carries activations only (load/store-bound layers: twice the useful bytes in flight)
   int w_bytes;     // bytes of the resident weight region
   int grid;        // persistent CTAs
+  uint32_t magic_n, magic_m;   // gemm_tc_magic() of N / BN and m_tiles: division-free tile decoding
+  int ctas_per_sm; // co-resident CTAs the launch is sized for (selects the register budget of the kernel variant)
   GemmProblem prob;
 };
 

@@ -41,6 +41,25 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
+// Tile coordinates without loop-carried state: tile = (img * m_tiles + mi) * n_tiles + nt, decoded per tile with the
+// host's multiply-high magic numbers (gemm_tc_magic): a handful of instructions instead of two integer divisions,
+// and no registers held across the tile loop (the hi-only epilogue runs at a 96-register budget).
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, uint32_t magic) {
+  if (magic == 0u) return n;                    // d == 1
+  if (magic == 0xffffffffu) return n / d;       // range too large for the 32-bit magic (host decides)
+  return __umulhi(n, magic);
+}
+struct TileCoord {
+  int nt, mi, img;
+  __device__ __forceinline__ TileCoord(uint32_t tile, const GemmTcParams& P, int n_tiles, int m_tiles) {
+    const uint32_t mt = fast_div(tile, (uint32_t)n_tiles, P.magic_n);
+    nt = (int)(tile - mt * (uint32_t)n_tiles);
+    const uint32_t im = fast_div(mt, (uint32_t)m_tiles, P.magic_m);
+    img = (int)im;
+    mi = (int)(mt - im * (uint32_t)m_tiles);
+  }
+};
+
 }  // namespace
 
 // Epilogue helpers: 32 fp32 values of one row -> packed half2 hi (and lo) words.
@@ -62,8 +81,10 @@ __device__ __forceinline__ void pack_hi_lo(const float (&v)[32], uint32_t (&hi)[
   }
 }
 
-template <int BN, int BK, int EPI_WARPS, bool THREE>
-__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 && EPI_WARPS == 4) ? 3 : (BN == 64 ? 2 : 1)))
+// MINB = co-resident CTAs per SM the register allocation is budgeted for (the engine picks the variant that
+// matches the occupancy shared memory allows: fewer CTAs -> more registers -> no spills in the 3-term epilogue).
+template <int BN, int BK, int EPI_WARPS, bool THREE, int MINB>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int ROW_BYTES = BK * 2;
@@ -71,6 +92,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
   constexpr int EPI_THREADS = 32 * EPI_WARPS;
   constexpr int CHUNK_STEP = EPI_WARPS / 4;             // column chunks are dealt to the warps of a lane quarter
   constexpr int NJ = (BN / 32 + CHUNK_STEP - 1) / CHUNK_STEP;   // chunks per epilogue warp
+  constexpr bool PREFETCH = !THREE && MINB == 1;        // residual planes one chunk ahead (needs 32 registers)
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // 1024-byte alignment by offset arithmetic (keeps the pointer in the shared address space: LDS/STS, not generic)
@@ -158,10 +180,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
       }
     }
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-      const int nt = tile % n_tiles, mt = tile / n_tiles;
-      const int img = mt / pr.m_tiles;
-      const int m0 = (mt - img * pr.m_tiles) * GEMM_BM;
-      const int n0 = nt * BN;
+      const TileCoord it((uint32_t)tile, P, n_tiles, pr.m_tiles);
+      const int img = it.img;
+      const int m0 = it.mi * GEMM_BM;
+      const int n0 = it.nt * BN;
       for (int t = 0; t < pr.ntaps && ok; ++t) {
         const GemmTap tap = pr.taps[t];
         const bool a_lo = THREE || tap.both;
@@ -191,7 +213,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
     constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
     constexpr uint32_t idesc2 = make_idesc_f16(GEMM_BM, THREE ? 2 * BN : BN);   // hi x [hi | lo]
     constexpr int ACC_W = THREE ? 2 * BN : BN;
-    int s = 0, ti = 0, g = 0;       // smem ring slot, tile counter, accumulation-segment counter
+    int s = 0, g = 0;               // smem ring slot, accumulation-segment counter
     uint32_t ph = 0;                // phase bit of the ring slot
     bool ok = true;
     if (w_res) {
@@ -199,7 +221,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
       tc_fence_after();
     }
     const uint32_t w_addr = smem_u32(w_base);
-    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       uint32_t d_main = 0, m_started = 0;
       uint32_t w_cur = w_addr;      // resident weights are consumed in the order they were loaded
       int left_in_tile = tile_chunks, left_in_seg = 0, buf = 0;   // countdowns: no division on the issue path
@@ -227,6 +249,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
             // +ROW_BYTES/16 per row of halo shift
             const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), da_lo0 = make_smem_desc(a_lo, ROW_BYTES);
             uint32_t started = m_started;
+#pragma unroll 1
             for (int gi = 0; gi < tg; ++gi) {
               const int sh = (gi == 0 ? sh0 : (gi == 1 ? sh1 : sh2)) * (ROW_BYTES / 16);
               const uint64_t db0 = make_smem_desc(w_res ? w_cur + gi * B_SLOT : a_hi + off_b + gi * B_SLOT, ROW_BYTES);   // spans [B_hi; B_lo]
@@ -266,9 +289,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
     // loop-invariant epilogue configuration in registers
     const int map = e.map, Wp = e.Wp, cout = e.cout, rows_in = e.rows_in;
-    const bool has_affine = e.a_scale != nullptr, has_bias = e.bias != nullptr;
-    const bool want_a = e.out_a.hi != nullptr, want_r = e.out_r.hi != nullptr, want_raw = e.out_raw != nullptr;
-    const bool has_resid = e.resid != nullptr, has_resid_planes = e.resid_hi != nullptr, has_head = e.head_w != nullptr;
+    // hi-only (1-term) kernels serve the vocoder: no BN affine, no fused head, no fp32 streams - compiled out, the
+    // 96-register budget of the two-CTA variants has no room for their state
+    const bool has_affine = THREE && e.a_scale != nullptr, has_bias = e.bias != nullptr;
+    const bool want_a = e.out_a.hi != nullptr, want_r = e.out_r.hi != nullptr, want_raw = THREE && e.out_raw != nullptr;
+    const bool has_resid = THREE && e.resid != nullptr, has_resid_planes = e.resid_hi != nullptr, has_head = THREE && e.head_w != nullptr;
     const int act = e.act;
     const float slope = e.slope;
     // lane roles for the row-major global accesses
@@ -284,15 +309,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
 #define SR_H(i) (32 * (i) + sr_h0 + (sr_hx ^ ((h_row >> 1) & 3)))
 #define SO_F(i) (so_f0 + ((i) ^ so_fx))
 #define SR_F(i) (32 * (i) + sr_f0 + (f_c16 ^ ((4 * (i) + f_row) & 7)))
-    const bool plain = !THREE && map == MAP_PLAIN;   // per-tile precomputed store indices (hi-only kernels)
-    int prev_n0 = -1, ti = 0, g = 0;
+    int prev_n0 = -1, g = 0;
     float amax = 0.f;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++ti) {
-      const int nt = tile % n_tiles, mt = tile / n_tiles;
-      const int img = mt / pr.m_tiles;
-      const int m0 = (mt - img * pr.m_tiles) * GEMM_BM;
-      const int n0 = nt * BN;
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      const TileCoord it((uint32_t)tile, P, n_tiles, pr.m_tiles);
+      const int img = it.img;
+      const int m0 = it.mi * GEMM_BM;
+      const int n0 = it.nt * BN;
       if (n0 != prev_n0) {   // per-N-tile constants (uniform branch)
         epi_bar_sync(EPI_THREADS);
         for (int i = et; i < BN; i += EPI_THREADS) {
@@ -306,37 +330,71 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
         epi_bar_sync(EPI_THREADS);
         prev_n0 = n0;
       }
-      const int r = m0 + q * 32 + lane;   // GEMM row inside the image
+      const int wrow0 = m0 + q * 32;      // first GEMM row (inside the image) of this warp's 32
+      const int r = wrow0 + lane;         // this thread's row
       const bool row_ok = r < rows_in;
       float head_acc = 0.f;
       int cth = 0, ctw = 0;
       uint32_t orow = 0, flags = 0;
-      // Fast path (MAP_PLAIN, i.e. everything but the transposed convs): the rows this lane stores / loads in the
-      // row-major phases are the same for every column chunk, so their element offsets (in 16-byte units) are
-      // computed once per tile; a chunk only adds its column offset.
-      uint32_t ia[4], ir[4];              // hi-only kernels only (3-term kernels need the registers for promotion)
-      uint32_t vh = 0;                    // valid-row bit mask of the 4 rows this lane stores
-      if (map == MAP_PLAIN) {             // row mapping independent of the column chunk
+      // MAP_PLAIN (everything but the transposed convs): output rows follow the GEMM rows, so the lanes that store
+      // row rr of this warp need no exchange: row = obase + rr, valid iff rr < lim.
+      const int lim = rows_in - wrow0;
+      const uint32_t obase = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + wrow0);
+      if (map == MAP_PLAIN) {
         if (row_ok) {
-          orow = (uint32_t)((size_t)img * e.out_img_rows + e.out_row0 + r);
+          orow = obase + lane;
           flags = kRowValid | ((Wp > 0 && (r % Wp) == Wp - 1) ? kRowPad : 0);
-        }
-        __syncwarp();
-        rows[lane] = RowInfo{orow, flags};
-        __syncwarp();
-        if (!THREE) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const RowInfo ri = rows[8 * i + h_row];
-            vh |= (ri.flags & kRowValid) ? (1u << i) : 0u;
-            ia[i] = (uint32_t)(((size_t)ri.orow * e.out_a.ld + e.out_a.c_off + n0) >> 3) + h_c16;
-            ir[i] = (uint32_t)(((size_t)ri.orow * e.out_r.ld + e.out_r.c_off + n0) >> 3) + h_c16;
-          }
         }
       } else if (map == MAP_CONVT2D) {
         cth = r / Wp;
         ctw = r - cth * Wp;
       }
+      // store this warp's staged 32 rows x 32 columns of fp16 (hi [+ lo]) row-major: 8 rows x 64 B per instruction
+      auto store_rows_h = [&](const OutPlane& op, const int co0, const bool two) {
+        if (map == MAP_PLAIN) {
+          const size_t o0 = (size_t)(obase + h_row) * op.ld + op.c_off + co0;   // one wide multiply per chunk
+          uint4* ph = reinterpret_cast<uint4*>(op.hi + o0) + h_c16;
+          uint4* pl = reinterpret_cast<uint4*>(op.lo + o0) + h_c16;
+          const int step = op.ld;       // 8 rows further, in 16-byte units
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (8 * i + h_row < lim) {
+              ph[i * step] = stg_h[SR_H(i)];
+              if (two) pl[i * step] = stg_l[SR_H(i)];
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const RowInfo ri = rows[8 * i + h_row];
+            if (ri.flags & kRowValid) {
+              const size_t o = (size_t)ri.orow * op.ld + op.c_off + co0;
+              reinterpret_cast<uint4*>(op.hi + o)[h_c16] = stg_h[SR_H(i)];
+              if (two) reinterpret_cast<uint4*>(op.lo + o)[h_c16] = stg_l[SR_H(i)];
+            }
+          }
+        }
+      };
+
+      // Residual planes of the NEXT column chunk are fetched into registers while the current one is processed
+      // (1-term kernels with a register budget for it): an epilogue warp otherwise has one exposed global-load
+      // round trip per chunk, which bounded voc.res*.b (ncu: 31 % of all samples on the first STS after the loads).
+      uint4 pre_h[4], pre_l[4];
+      auto load_resid = [&](const int j) {     // MAP_PLAIN only (the residual stream follows the GEMM rows)
+        const size_t rbase = ((size_t)img * rows_in + wrow0 + h_row) * e.resid_ld + n0 + j * 32;
+        const uint4* gh = reinterpret_cast<const uint4*>(e.resid_hi + rbase) + h_c16;
+        const uint4* gl = reinterpret_cast<const uint4*>(e.resid_lo + rbase) + h_c16;
+        const int step = e.resid_ld;     // 8 rows further, in 16-byte units
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pre_h[i] = make_uint4(0, 0, 0, 0);
+          pre_l[i] = make_uint4(0, 0, 0, 0);
+          if (8 * i + h_row < lim) {
+            pre_h[i] = __ldg(gh + i * step);
+            pre_l[i] = __ldg(gl + i * step);
+          }
+        }
+      };
+      if (PREFETCH && has_resid_planes) load_resid(half);
 
       // One 32-column chunk of this thread's row: bias, residual, outputs (see gemm.cuh for the semantics).
       auto process_chunk = [&](const int j, float (&v)[32]) {
@@ -389,18 +447,27 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
           }
         }
         if (has_resid_planes) {           // residual stream kept as hi/lo planes: coalesced load, sum in fp32
-          const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
           __syncwarp();
+          if (PREFETCH) {                 // loaded one chunk ahead (see load_resid below): no exposed load latency
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + h_row;
-            uint4 xh = make_uint4(0, 0, 0, 0), xl = make_uint4(0, 0, 0, 0);
-            if (m0 + q * 32 + rr < rows_in) {
-              xh = __ldg(reinterpret_cast<const uint4*>(e.resid_hi + rbase + (size_t)rr * e.resid_ld) + h_c16);
-              xl = __ldg(reinterpret_cast<const uint4*>(e.resid_lo + rbase + (size_t)rr * e.resid_ld) + h_c16);
+            for (int i = 0; i < 4; ++i) {
+              stg_h[SR_H(i)] = pre_h[i];
+              stg_l[SR_H(i)] = pre_l[i];
             }
-            stg_h[SR_H(i)] = xh;
-            stg_l[SR_H(i)] = xl;
+            if (j + CHUNK_STEP < BN / 32) load_resid(j + CHUNK_STEP);
+          } else {
+            const size_t rbase = ((size_t)img * rows_in + wrow0) * e.resid_ld + co0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + h_row;
+              uint4 xh = make_uint4(0, 0, 0, 0), xl = make_uint4(0, 0, 0, 0);
+              if (rr < lim) {
+                xh = __ldg(reinterpret_cast<const uint4*>(e.resid_hi + rbase + (size_t)rr * e.resid_ld) + h_c16);
+                xl = __ldg(reinterpret_cast<const uint4*>(e.resid_lo + rbase + (size_t)rr * e.resid_ld) + h_c16);
+              }
+              stg_h[SR_H(i)] = xh;
+              stg_l[SR_H(i)] = xl;
+            }
           }
           __syncwarp();
 #pragma unroll
@@ -426,12 +493,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
 #pragma unroll
           for (int i = 0; i < 8; ++i) stg_f[SO_F(i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           __syncwarp();
+          if (map == MAP_PLAIN) {
+            float4* pr4 = reinterpret_cast<float4*>(e.out_raw + (size_t)(obase + f_row) * e.raw_ld + co0) + f_c16;
+            const int step = e.raw_ld;    // 4 rows further, in 16-byte units
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + f_row;
-            const RowInfo ri = rows[rr];
-            if (ri.flags & kRowValid)
-              reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[SR_F(i)];
+            for (int i = 0; i < 8; ++i)
+              if (4 * i + f_row < lim) pr4[i * step] = stg_f[SR_F(i)];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const RowInfo ri = rows[4 * i + f_row];
+              if (ri.flags & kRowValid)
+                reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[SR_F(i)];
+            }
           }
         }
         if (want_r) {                     // raw hi/lo planes
@@ -444,24 +518,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
             stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
-          if (plain) {
-            uint4* ph = reinterpret_cast<uint4*>(e.out_r.hi) + j * 4;
-            uint4* pl = reinterpret_cast<uint4*>(e.out_r.lo) + j * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if ((vh >> i) & 1u) { ph[ir[i]] = stg_h[SR_H(i)]; pl[ir[i]] = stg_l[SR_H(i)]; }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = 8 * i + h_row;
-              const RowInfo ri = rows[rr];
-              if (ri.flags & kRowValid) {
-                const size_t o = (size_t)ri.orow * e.out_r.ld + e.out_r.c_off + co0;
-                reinterpret_cast<uint4*>(e.out_r.hi + o)[h_c16] = stg_h[SR_H(i)];
-                reinterpret_cast<uint4*>(e.out_r.lo + o)[h_c16] = stg_l[SR_H(i)];
-              }
-            }
-          }
+          store_rows_h(e.out_r, co0, true);
         }
         if (has_head) {                   // fused 1x1 head (N == 32)
 #pragma unroll
@@ -502,27 +559,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
             if (THREE) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
-          if (plain) {
-            uint4* ph = reinterpret_cast<uint4*>(e.out_a.hi) + j * 4;
-            uint4* pl = reinterpret_cast<uint4*>(e.out_a.lo) + j * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if ((vh >> i) & 1u) {
-                ph[ia[i]] = stg_h[SR_H(i)];
-                if (THREE) pl[ia[i]] = stg_l[SR_H(i)];
-              }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = 8 * i + h_row;
-              const RowInfo ri = rows[rr];
-              if (ri.flags & kRowValid) {
-                const size_t o = (size_t)ri.orow * e.out_a.ld + e.out_a.c_off + co0;
-                reinterpret_cast<uint4*>(e.out_a.hi + o)[h_c16] = stg_h[SR_H(i)];
-                if (THREE) reinterpret_cast<uint4*>(e.out_a.lo + o)[h_c16] = stg_l[SR_H(i)];
-              }
-            }
-          }
+          store_rows_h(e.out_a, co0, THREE);
         }
       };
 
@@ -568,13 +605,15 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
         for (int j = half; j < BN / 32; j += CHUNK_STEP) {
           float v[32];
           tmem_ld_32x32(tmem_base + lane_bits + buf * BN + j * 32, v);
+          if (j + CHUNK_STEP >= BN / 32) {   // last chunk is in registers: hand the accumulator back before the math / stores
+            tc_fence_before();
+            mbar_arrive(seg_empty_bar + buf);
+          }
           process_chunk(j, v);
         }
-        tc_fence_before();
-        mbar_arrive(seg_empty_bar + buf);
         ++g;
       }
-      if (half == 0) epilogue_head(e, img, r, head_acc);
+      if (THREE && half == 0) epilogue_head(e, img, r, head_acc);
     }
     // NaN compares false against everything, inf exceeds the bound
     if (!(amax <= 65504.f) && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
@@ -588,9 +627,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, (BN == 32 || (BN == 64 &&
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static bool g_bn64_ew4 = false;   // tuning experiment: BN = 64 hi-only tiles with 4 epilogue warps, 3 CTAs per SM
-void gemm_tc_set_bn64_ew4(bool on) { g_bn64_ew4 = on; }
-static int epi_warps_for(int bn, int terms) { return (bn == 32 || (bn == 64 && terms == 1 && g_bn64_ew4)) ? 4 : 8; }
+static int epi_warps_for(int bn, int /*terms*/) { return bn == 32 ? 4 : 8; }
 
 size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes) {
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
@@ -599,35 +636,45 @@ size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, i
   return stages * stage + w_bytes + ew * 4096 + (2 * stages + 6) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
 }
 
-template <int BN, int BK, int EW, bool THREE>
+template <int BN, int BK, int EW, bool THREE, int MINB>
 static cudaError_t launch_cfg(const GemmTcParams& p, cudaStream_t stream) {
   const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax, p.w_resident ? p.w_bytes : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW, THREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW, THREE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<BN, BK, EW, THREE><<<p.grid, 64 + 32 * EW, smem, stream>>>(p);
+  gemm_tc_kernel<BN, BK, EW, THREE, MINB><<<p.grid, 64 + 32 * EW, smem, stream>>>(p);
   return cudaGetLastError();
 }
-template <int BN, int BK, int EW>
+template <int BN, int BK, int EW, int MINB>
 static cudaError_t launch_one(const GemmTcParams& p, cudaStream_t stream) {
-  return p.prob.terms == 3 ? launch_cfg<BN, BK, EW, true>(p, stream) : launch_cfg<BN, BK, EW, false>(p, stream);
+  return p.prob.terms == 3 ? launch_cfg<BN, BK, EW, true, MINB>(p, stream) : launch_cfg<BN, BK, EW, false, MINB>(p, stream);
+}
+template <int BK>
+static cudaError_t launch_bk(const GemmTcParams& p, int bn, cudaStream_t stream) {
+  const int c = p.ctas_per_sm;
+  if (bn == 256) return p.prob.terms == 1 ? launch_cfg<256, BK, 8, false, 1>(p, stream) : cudaErrorInvalidValue;
+  if (bn == 128) return launch_one<128, BK, 8, 1>(p, stream);
+  if (bn == 64) return c >= 2 ? launch_one<64, BK, 8, 2>(p, stream) : launch_one<64, BK, 8, 1>(p, stream);
+  if (bn == 32) return c >= 3 ? launch_one<32, BK, 4, 3>(p, stream) : launch_one<32, BK, 4, 2>(p, stream);
+  return cudaErrorInvalidValue;
 }
 
+// multiply-high magic for n / d with n <= nmax: exact while nmax * d < 2^32 (the error term of ceil(2^32 / d))
+uint32_t gemm_tc_magic(uint32_t d, uint64_t nmax) {
+  if (d <= 1) return 0u;
+  if (nmax * (uint64_t)d >= (1ull << 32)) return 0xffffffffu;
+  return (uint32_t)(((1ull << 32) + d - 1) / d);
+}
+
+// register-limited CTAs per SM of the variants above (the engine sizes shared memory and the grid against it)
+int gemm_tc_max_ctas(int bn) { return bn == 32 ? 3 : (bn == 64 ? 2 : 1); }
+
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream) {
-  if (bk == 64) {
-    if (bn == 256) return p.prob.terms == 1 ? launch_cfg<256, 64, 8, false>(p, stream) : cudaErrorInvalidValue;
-    if (bn == 128) return launch_one<128, 64, 8>(p, stream);
-    if (bn == 64) return (p.prob.terms == 1 && g_bn64_ew4) ? launch_cfg<64, 64, 4, false>(p, stream) : launch_one<64, 64, 8>(p, stream);
-    if (bn == 32) return launch_one<32, 64, 4>(p, stream);
-  } else if (bk == 32) {
-    if (bn == 256) return p.prob.terms == 1 ? launch_cfg<256, 32, 8, false>(p, stream) : cudaErrorInvalidValue;
-    if (bn == 128) return launch_one<128, 32, 8>(p, stream);
-    if (bn == 64) return (p.prob.terms == 1 && g_bn64_ew4) ? launch_cfg<64, 32, 4, false>(p, stream) : launch_one<64, 32, 8>(p, stream);
-    if (bn == 32) return launch_one<32, 32, 4>(p, stream);
-  }
+  if (bk == 64) return launch_bk<64>(p, bn, stream);
+  if (bk == 32) return launch_bk<32>(p, bn, stream);
   return cudaErrorInvalidValue;
 }
 
