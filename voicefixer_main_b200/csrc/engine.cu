@@ -25,7 +25,7 @@
 
 namespace vf {
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes);
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int tile_chunks);
 int gemm_tc_max_ctas(int bn);
 uint32_t gemm_tc_magic(uint32_t d, uint64_t nmax);
 cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
@@ -587,7 +587,9 @@ struct Builder {
           i += n;
         }
         // a grouped stage holds up to 3 weight tiles: keep the grouping only if a 2-deep ring still fits
-        if (gm > 1 && gemm_tc_smem_bytes(bn, bk, 2, (terms == 3 || any_both) ? 2 : 1, terms, GEMM_BM + 2, gm, 0) <= (size_t)226 * 1024) {
+        int gchunks = 0;
+        for (auto& t : grouped) gchunks += t.nch / bk;
+        if (gm > 1 && gemm_tc_smem_bytes(bn, bk, 2, (terms == 3 || any_both) ? 2 : 1, terms, GEMM_BM + 2, gm, gchunks) <= (size_t)226 * 1024) {
           taps.swap(grouped);
           gmax = gm;
         }
@@ -654,34 +656,12 @@ struct Builder {
         if (const char* ov = getenv(key)) { if (k <= 1024) ctas = std::max(1, std::min(reg_limit, atoi(ov))); }
       }
       int stages = 0;
-      // weight-stationary: one N tile, load/store-bound layer, weights + a ring of >= 2 tiles of activations fit
-      int n_wslots = 0;
-      for (auto& t : taps) n_wslots += (t.nch / bk) * t.g;
-      const int w_bytes = n_wslots * (terms == 3 ? 2 : 1) * bn * bk * 2;
-      // measured: slower than 2-3 co-resident CTAs streaming weights from L2 (the epilogue, not the ring depth,
-      // limits these layers) - kept as an opt-in experiment (VF_TUNE_WRES=1|2)
-      bool w_res = false;
-      if (const char* ov = getenv("VF_TUNE_WRES")) w_res = N == bn && k <= 1024 && w_bytes <= 100 * 1024 && (atoi(ov) == 2 || (atoi(ov) == 1 && terms == 1));
-      if (w_res) {
-        bool found = false;
-        tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
-        for (int c = ctas; c >= 1 && !found; --c) {
-          if (tp.tmem_cols * c > 512) continue;
-          const size_t per_cta = (size_t)227 * 1024 / c - 1024;
-          for (stages = 12; stages >= 3; --stages)
-            if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, w_bytes) <= per_cta) break;
-          if (stages >= 3) { ctas = c; found = true; }
-        }
-        if (!found) w_res = false;
-      }
-      tp.w_resident = w_res ? 1 : 0;
-      tp.w_bytes = w_res ? w_bytes : 0;
-      for (; !w_res && ctas >= 1; --ctas) {
+      for (; ctas >= 1; --ctas) {
         tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
         if (tp.tmem_cols * ctas > 512) continue;
         const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
         for (stages = 8; stages >= 2; --stages)
-          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, 0) <= per_cta) break;
+          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, tp.tile_chunks) <= per_cta) break;
         if (stages >= 2) break;
       }
       if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }

@@ -105,9 +105,6 @@ struct GemmTcParams {
   int planes_a;    // smem slots per stage for A: 2 when any tap contracts the lo plane
   int a_box_rows;  // rows per A TMA box: 128, or 130 when taps are grouped (halo)
   int gmax;        // largest tap group: B slots per stage
-  int w_resident;  // 1: the whole weight slice (single N tile) is loaded into shared memory once per CTA and the
-                   //    ring carries activations only (load/store-bound layers: twice the useful bytes in flight)
-  int w_bytes;     // bytes of the resident weight region
   int grid;        // persistent CTAs
   uint32_t magic_n, magic_m;   // gemm_tc_magic() of N / BN and m_tiles: division-free tile decoding
   int ctas_per_sm; // co-resident CTAs the launch is sized for (selects the register budget of the kernel variant)

@@ -41,6 +41,16 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
+// One K chunk (= one ring slot) of a tile, as the two issue threads need it: the tap structure is flattened once per
+// CTA into this table, so the per-chunk work of the producer / MMA loops is one 16-byte shared-memory load instead
+// of a walk over the tap list in constant memory.
+struct ChunkDesc {
+  int a_c;          // channel coordinate of the A box
+  int a_off;        // row offset of the A box relative to the tile's first row
+  uint32_t kk;      // K coordinate of the first weight tile | kstride << 16 (stride between the weight tiles of a group)
+  uint32_t flags;   // bit 0 src, bit 1 lo plane of A is needed, bits 2-3 g, bit 4 both, bits 5-6 / 7-8 / 9-10 row shifts
+};
+
 // Tile coordinates without loop-carried state: tile = (img * m_tiles + mi) * n_tiles + nt, decoded per tile with the
 // host's multiply-high magic numbers (gemm_tc_magic): a handful of instructions instead of two integer divisions,
 // and no registers held across the tile loop (the hi-only epilogue runs at a 96-register budget).
@@ -92,6 +102,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
   constexpr int EPI_THREADS = 32 * EPI_WARPS;
   constexpr int CHUNK_STEP = EPI_WARPS / 4;             // column chunks are dealt to the warps of a lane quarter
   constexpr int NJ = (BN / 32 + CHUNK_STEP - 1) / CHUNK_STEP;   // chunks per epilogue warp
+  // the fully unrolled tap-group loop of the MMA issuer costs registers kernel-wide: rolled where the budget is 96
+  constexpr int GI_UNROLL = (!THREE && MINB >= 2) ? 1 : 3;
   constexpr bool PREFETCH = !THREE && MINB == 1;        // residual planes one chunk ahead (needs 32 registers)
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -103,22 +115,20 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
   const int a_box_bytes = P.a_box_rows * ROW_BYTES;     // bytes one A TMA box delivers
   const int a_slot = (a_box_bytes + 1023) & ~1023;      // halo rows spill into one more swizzle atom
   const int off_b = planes_a * a_slot;
-  const bool w_res = P.w_resident != 0;
-  const int stage_bytes = off_b + (w_res ? 0 : P.gmax * B_SLOT);
-  uint8_t* w_base = smem + (size_t)stages * stage_bytes;            // resident weights (w_resident), else empty
-  uint8_t* stg_base = w_base + P.w_bytes;                           // EPI_WARPS x 4 KB staging
+  const int stage_bytes = off_b + P.gmax * B_SLOT;
+  uint8_t* stg_base = smem + (size_t)stages * stage_bytes;          // EPI_WARPS x 4 KB staging
   uint8_t* tail = stg_base + EPI_WARPS * 4096;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* seg_full_bar = empty_bar + stages;           // [2] main accumulator buffer holds a finished segment
   uint64_t* seg_empty_bar = seg_full_bar + 2;            // [2] ... has been drained by every epilogue thread
-  uint64_t* w_full_bar = seg_empty_bar + 2;              // resident weights have landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full_bar + 2);   // keep the float arrays 16-byte aligned
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(seg_empty_bar + 4);   // keep the float arrays 16-byte aligned
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
-  float* s_shift = s_scale + BN;                               // [BN]
+  float* s_shift = s_scale + BN;                                // [BN]
   float* s_head = s_shift + BN;                                // [32]
   RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_head + 32);   // [EPI_WARPS * 32]
+  ChunkDesc* s_tab = reinterpret_cast<ChunkDesc*>(s_rows + EPI_WARPS * 32);   // [tile_chunks], 16-byte aligned
 
   const GemmProblem& pr = P.prob;
   const GemmEpilogue& e = pr.epi;
@@ -141,7 +151,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
       mbar_init(seg_full_bar + i, 1);
       mbar_init(seg_empty_bar + i, EPI_THREADS);
     }
-    mbar_init(w_full_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
     tma_prefetch_desc(&P.b_hi);
@@ -151,6 +160,23 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     }
   }
   if (warp == 1) tmem_alloc_dyn(tmem_holder, P.tmem_cols);
+  for (int ci = threadIdx.x; ci < tile_chunks; ci += blockDim.x) {   // flatten taps x K chunks (see ChunkDesc)
+    int t = 0, first = 0;
+    for (; t < pr.ntaps - 1; ++t) {
+      const int n = pr.taps[t].nch / BK;
+      if (ci < first + n) break;
+      first += n;
+    }
+    const GemmTap& tap = pr.taps[t];
+    const int c = (ci - first) * BK;
+    ChunkDesc cd;
+    cd.a_c = tap.c_off + c;
+    cd.a_off = tap.a_off;
+    cd.kk = (uint32_t)(tap.k_off + c) | ((uint32_t)tap.kstride << 16);
+    cd.flags = (uint32_t)(tap.src & 1) | ((THREE || tap.both) ? 2u : 0u) | ((uint32_t)tap.g << 2) | (tap.both ? 16u : 0u) |
+               ((uint32_t)tap.shift[0] << 5) | ((uint32_t)tap.shift[1] << 7) | ((uint32_t)tap.shift[2] << 9);
+    s_tab[ci] = cd;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,42 +193,30 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     int s = 0;              // ring slot and its phase bit advance by increment: no division on the issue path
     uint32_t ph = 0;
     bool ok = true;
-    if (w_res) {            // weight-stationary: the single N tile's weights, chunk by chunk in MMA order
-      mbar_expect_tx(w_full_bar, (uint32_t)P.w_bytes);
-      uint8_t* wp = w_base;
-      for (int t = 0; t < pr.ntaps; ++t) {
-        const GemmTap tap = pr.taps[t];
-        for (int c = 0; c < tap.nch; c += BK)
-          for (int gi = 0; gi < tap.g; ++gi, wp += B_SLOT) {
-            tma_load_2d(wp, &P.b_hi, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
-            if (THREE) tma_load_2d(wp + B_BYTES, &P.b_lo, w_full_bar, tap.k_off + gi * tap.kstride + c, 0);
-          }
-      }
-    }
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       const TileCoord it((uint32_t)tile, P, n_tiles, pr.m_tiles);
       const int img = it.img;
       const int m0 = it.mi * GEMM_BM;
       const int n0 = it.nt * BN;
-      for (int t = 0; t < pr.ntaps && ok; ++t) {
-        const GemmTap tap = pr.taps[t];
-        const bool a_lo = THREE || tap.both;
-        const uint32_t tx = (a_lo ? 2u : 1u) * a_box_bytes + (w_res ? 0 : tap.g * B_SLOT);
-        for (int c = 0; c < tap.nch; c += BK) {
-          if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
-          {
-            uint8_t* st = smem + (size_t)s * stage_bytes;
-            mbar_expect_tx(full_bar + s, tx);
-            tma_load_3d(st, &P.a_hi[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-            if (a_lo) tma_load_3d(st + a_slot, &P.a_lo[tap.src], full_bar + s, tap.c_off + c, m0 + tap.a_off, img);
-            for (int gi = 0; gi < tap.g && !w_res; ++gi) {
-              uint8_t* sb = st + off_b + gi * B_SLOT;
-              tma_load_2d(sb, &P.b_hi, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
-              if (THREE) tma_load_2d(sb + B_BYTES, &P.b_lo, full_bar + s, tap.k_off + gi * tap.kstride + c, n0);
-            }
-          }
-          if (++s == stages) { s = 0; ph ^= 1; }
+      ChunkDesc cd = s_tab[0];
+      for (int ci = 0; ci < tile_chunks; ++ci) {
+        const ChunkDesc cur = cd;
+        cd = s_tab[ci + 1 < tile_chunks ? ci + 1 : 0];     // next entry: its load latency hides behind the wait
+        if (!mbar_wait(empty_bar + s, ph ^ 1, e.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+        const bool a_lo = (cur.flags & 2u) != 0;
+        const int src = cur.flags & 1u;
+        const int tg = (cur.flags >> 2) & 3u;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(full_bar + s, (a_lo ? 2u : 1u) * a_box_bytes + tg * B_SLOT);
+        tma_load_3d(st, &P.a_hi[src], full_bar + s, cur.a_c, m0 + cur.a_off, img);
+        if (a_lo) tma_load_3d(st + a_slot, &P.a_lo[src], full_bar + s, cur.a_c, m0 + cur.a_off, img);
+        const int k0 = cur.kk & 0xffffu, ks = cur.kk >> 16;
+        for (int gi = 0; gi < tg; ++gi) {
+          uint8_t* sb = st + off_b + gi * B_SLOT;
+          tma_load_2d(sb, &P.b_hi, full_bar + s, k0 + gi * ks, n0);
+          if (THREE) tma_load_2d(sb + B_BYTES, &P.b_lo, full_bar + s, k0 + gi * ks, n0);
         }
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
     }
@@ -216,62 +230,49 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     int s = 0, g = 0;               // smem ring slot, accumulation-segment counter
     uint32_t ph = 0;                // phase bit of the ring slot
     bool ok = true;
-    if (w_res) {
-      ok = mbar_wait(w_full_bar, 0, e.err, ERR_PIPE_MMA);
-      tc_fence_after();
-    }
-    const uint32_t w_addr = smem_u32(w_base);
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-      uint32_t d_main = 0, m_started = 0;
-      uint32_t w_cur = w_addr;      // resident weights are consumed in the order they were loaded
-      int left_in_tile = tile_chunks, left_in_seg = 0, buf = 0;   // countdowns: no division on the issue path
-      for (int t = 0; t < pr.ntaps && ok; ++t) {
-        const int nch = pr.taps[t].nch;
-        const bool both = pr.taps[t].both != 0;
-        const int tg = pr.taps[t].g;
-        const int sh0 = pr.taps[t].shift[0], sh1 = pr.taps[t].shift[1], sh2 = pr.taps[t].shift[2];
-        for (int c = 0; c < nch; c += BK) {
-          if (left_in_seg == 0) {              // open a segment: its accumulator buffer must have been drained
-            left_in_seg = min(seg_chunks, left_in_tile);
-            buf = g & 1;
-            if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
-            d_main = tmem_base + buf * ACC_W;
-            m_started = 0;
-          }
-          if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
-          tc_fence_after();
-          --left_in_tile;
-          const bool close_seg = --left_in_seg == 0;
-          {
-            const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint32_t a_lo = a_hi + a_slot;
-            // descriptors differ only in the 14-bit start-address field (units of 16 B): +2 per 32-byte K step,
-            // +ROW_BYTES/16 per row of halo shift
-            const uint64_t da_hi0 = make_smem_desc(a_hi, ROW_BYTES), da_lo0 = make_smem_desc(a_lo, ROW_BYTES);
-            uint32_t started = m_started;
-#pragma unroll 1
-            for (int gi = 0; gi < tg; ++gi) {
-              const int sh = (gi == 0 ? sh0 : (gi == 1 ? sh1 : sh2)) * (ROW_BYTES / 16);
-              const uint64_t db0 = make_smem_desc(w_res ? w_cur + gi * B_SLOT : a_hi + off_b + gi * B_SLOT, ROW_BYTES);   // spans [B_hi; B_lo]
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                umma_f16(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, idesc2, started);
-                started = 1;
-                if (THREE) {
-                  umma_f16(d_main + BN, da_lo0 + sh + 2 * k, db0 + 2 * k, idesc, 1u);
-                } else if (both) {
-                  umma_f16(d_main, da_lo0 + sh + 2 * k, db0 + 2 * k, idesc, 1u);
-                }
-              }
-            }
-            umma_commit(empty_bar + s);              // frees the smem slot once these MMAs have read it
-            if (close_seg) umma_commit(seg_full_bar + buf);
-          }
-          m_started = 1;
-          w_cur += tg * B_SLOT;
-          if (close_seg) ++g;
-          if (++s == stages) { s = 0; ph ^= 1; }
+      uint32_t d_main = 0, started = 0;
+      int left_in_seg = 0, buf = 0;                      // countdown: no division on the issue path
+      uint32_t fl = s_tab[0].flags;
+      for (int ci = 0; ci < tile_chunks; ++ci) {
+        const uint32_t cur = fl;
+        fl = s_tab[ci + 1 < tile_chunks ? ci + 1 : 0].flags;
+        if (left_in_seg == 0) {                // open a segment: its accumulator buffer must have been drained
+          left_in_seg = min(seg_chunks, tile_chunks - ci);
+          buf = g & 1;
+          if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+          d_main = tmem_base + buf * ACC_W;
+          started = 0;
         }
+        if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+        tc_fence_after();
+        const bool close_seg = --left_in_seg == 0;
+        // descriptors differ only in the 14-bit start-address field of their low word (units of 16 B): +2 per
+        // 32-byte K step, +ROW_BYTES/16 per row of halo shift, +B_SLOT/16 per weight tile of a tap group
+        constexpr uint32_t dhi = make_smem_desc_hi(ROW_BYTES);
+        const uint32_t da_hi0 = make_smem_desc_lo(smem_u32(smem + (size_t)s * stage_bytes));
+        const uint32_t da_lo0 = da_hi0 + (uint32_t)(a_slot >> 4);
+        const uint32_t db00 = da_hi0 + (uint32_t)(off_b >> 4);                 // spans [B_hi; B_lo]
+        const int tg = (cur >> 2) & 3u;
+        const bool both = (cur & 16u) != 0;
+#pragma unroll GI_UNROLL
+        for (int gi = 0; gi < tg; ++gi) {
+          const uint32_t sh = ((cur >> (5 + 2 * gi)) & 3u) * (ROW_BYTES / 16);
+          const uint32_t db0 = db00 + (uint32_t)(gi * (B_SLOT / 16));
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
+            umma_f16_lo(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, dhi, idesc2, started);
+            started = 1;
+            if (THREE) {
+              umma_f16_lo(d_main + BN, da_lo0 + sh + 2 * k, db0 + 2 * k, dhi, idesc, 1u);
+            } else if (both) {
+              umma_f16_lo(d_main, da_lo0 + sh + 2 * k, db0 + 2 * k, dhi, idesc, 1u);
+            }
+          }
+        }
+        umma_commit(empty_bar + s);              // frees the smem slot once these MMAs have read it
+        if (close_seg) { umma_commit(seg_full_bar + buf); ++g; }
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
     }
@@ -629,16 +630,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
 // ---------------------------------------------------------------------------------------------- host side
 static int epi_warps_for(int bn, int /*terms*/) { return bn == 32 ? 4 : 8; }
 
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int w_bytes) {
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int tile_chunks) {
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
-  const size_t stage = planes_a * a_slot + (w_bytes ? 0 : (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2);
+  const size_t stage = planes_a * a_slot + (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2;
   const int ew = epi_warps_for(bn, terms);
-  return stages * stage + w_bytes + ew * 4096 + (2 * stages + 6) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + 1024;
+  return stages * stage + ew * 4096 + (2 * stages + 6) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + (size_t)tile_chunks * 16 + 1024;
 }
 
 template <int BN, int BK, int EW, bool THREE, int MINB>
 static cudaError_t launch_cfg(const GemmTcParams& p, cudaStream_t stream) {
-  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax, p.w_resident ? p.w_bytes : 0);
+  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax, p.tile_chunks);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW, THREE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -112,6 +112,20 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors given as their low words plus the shared high word (make_smem_desc_hi): all per-MMA
+// descriptor arithmetic (K step, halo row shift, weight tile) touches only the 14-bit start-address field, so the
+// issue loop advances 32-bit values instead of 64-bit ones with carries.
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -145,6 +159,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, int row_b
   d |= static_cast<uint64_t>(1) << 46;                                   // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61;            // swizzle mode
   return d;
+}
+__device__ __forceinline__ uint32_t make_smem_desc_lo(uint32_t smem_addr) {      // start address >> 4 | LBO
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__host__ __device__ constexpr uint32_t make_smem_desc_hi(int row_bytes) {        // SBO | version | swizzle mode
+  return static_cast<uint32_t>((8 * row_bytes) >> 4) | (1u << 14) | (static_cast<uint32_t>(row_bytes == 128 ? 2 : 4) << 29);
 }
 // cute::UMMA::InstrDescriptor for kind::f16: C=F32 (1<<4), A=B=F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
