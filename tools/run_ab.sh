@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 while [ $# -ge 2 ]; do
   name=$1; envs=$2; shift 2
   par=$(env $envs timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x --tb=line -k "golden or vocoder_vs or tcgen05" 2>&1 | tail -1)
-  env $envs timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/ab_$name.json 2>&1 | tail -1 > gpurun_out/ab_$name.line
+  env $envs timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/ab_$name.json 2>&1 | tail -1 > gpurun_out/ab_$name.line
   python - "$name" "$par" <<'PY'
 import json, sys
 name, par = sys.argv[1], sys.argv[2]

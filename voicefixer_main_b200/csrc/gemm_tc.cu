@@ -91,6 +91,29 @@ __device__ __forceinline__ void pack_hi_lo(const float (&v)[32], uint32_t (&hi)[
   }
 }
 
+// The MMAs of one K chunk: G taps (row shifts packed 2 bits each in `shifts`) x BK/16 K steps; 3-term mode adds
+// lo(A) x hi(B) into the correction half, BOTH (hi-only identity tap) contracts the lo plane into the same accumulator.
+template <int BN, int BK, bool THREE, int G, bool BOTH>
+__device__ __forceinline__ void issue_mmas(uint32_t d_main, uint32_t da_hi0, uint32_t da_lo0, uint32_t db00, uint32_t shifts,
+                                           uint32_t started) {
+  constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
+  constexpr uint32_t idesc2 = make_idesc_f16(GEMM_BM, THREE ? 2 * BN : BN);   // hi x [hi | lo]
+  constexpr uint32_t dhi = make_smem_desc_hi(BK * 2);
+  constexpr uint32_t ROW_UNITS = BK * 2 / 16;
+  constexpr uint32_t B_SLOT_UNITS = (THREE ? 2 : 1) * BN * BK * 2 / 16;
+#pragma unroll 1
+  for (int gi = 0; gi < G; ++gi) {
+    const uint32_t sh = G == 1 ? 0u : ((shifts >> (2 * gi)) & 3u) * ROW_UNITS;
+    const uint32_t db0 = db00 + gi * B_SLOT_UNITS;
+#pragma unroll
+    for (int k = 0; k < BK / 16; ++k) {
+      umma_f16_lo(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, dhi, idesc2, (gi == 0 && k == 0) ? started : 1u);
+      if (THREE) umma_f16_lo(d_main + BN, da_lo0 + sh + 2 * k, db0 + 2 * k, dhi, idesc, 1u);
+      else if (BOTH) umma_f16_lo(d_main, da_lo0 + sh + 2 * k, db0 + 2 * k, dhi, idesc, 1u);
+    }
+  }
+}
+
 // MINB = co-resident CTAs per SM the register allocation is budgeted for (the engine picks the variant that
 // matches the occupancy shared memory allows: fewer CTAs -> more registers -> no spills in the 3-term epilogue).
 template <int BN, int BK, int EPI_WARPS, bool THREE, int MINB>
@@ -98,12 +121,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     gemm_tc_kernel(const __grid_constant__ GemmTcParams P) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int ROW_BYTES = BK * 2;
-  constexpr int KSTEPS = BK / 16;
   constexpr int EPI_THREADS = 32 * EPI_WARPS;
   constexpr int CHUNK_STEP = EPI_WARPS / 4;             // column chunks are dealt to the warps of a lane quarter
   constexpr int NJ = (BN / 32 + CHUNK_STEP - 1) / CHUNK_STEP;   // chunks per epilogue warp
-  // the fully unrolled tap-group loop of the MMA issuer costs registers kernel-wide: rolled where the budget is 96
-  constexpr int GI_UNROLL = (!THREE && MINB >= 2) ? 1 : 3;
   constexpr bool PREFETCH = !THREE && MINB == 1;        // residual planes one chunk ahead (needs 32 registers)
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -224,8 +244,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-    constexpr uint32_t idesc = make_idesc_f16(GEMM_BM, BN);
-    constexpr uint32_t idesc2 = make_idesc_f16(GEMM_BM, THREE ? 2 * BN : BN);   // hi x [hi | lo]
     constexpr int ACC_W = THREE ? 2 * BN : BN;
     int s = 0, g = 0;               // smem ring slot, accumulation-segment counter
     uint32_t ph = 0;                // phase bit of the ring slot
@@ -249,27 +267,22 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         const bool close_seg = --left_in_seg == 0;
         // descriptors differ only in the 14-bit start-address field of their low word (units of 16 B): +2 per
         // 32-byte K step, +ROW_BYTES/16 per row of halo shift, +B_SLOT/16 per weight tile of a tap group
-        constexpr uint32_t dhi = make_smem_desc_hi(ROW_BYTES);
         const uint32_t da_hi0 = make_smem_desc_lo(smem_u32(smem + (size_t)s * stage_bytes));
         const uint32_t da_lo0 = da_hi0 + (uint32_t)(a_slot >> 4);
         const uint32_t db00 = da_hi0 + (uint32_t)(off_b >> 4);                 // spans [B_hi; B_lo]
-        const int tg = (cur >> 2) & 3u;
-        const bool both = (cur & 16u) != 0;
-#pragma unroll GI_UNROLL
-        for (int gi = 0; gi < tg; ++gi) {
-          const uint32_t sh = ((cur >> (5 + 2 * gi)) & 3u) * (ROW_BYTES / 16);
-          const uint32_t db0 = db00 + (uint32_t)(gi * (B_SLOT / 16));
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            umma_f16_lo(d_main, da_hi0 + sh + 2 * k, db0 + 2 * k, dhi, idesc2, started);
-            started = 1;
-            if (THREE) {
-              umma_f16_lo(d_main + BN, da_lo0 + sh + 2 * k, db0 + 2 * k, dhi, idesc, 1u);
-            } else if (both) {
-              umma_f16_lo(d_main, da_lo0 + sh + 2 * k, db0 + 2 * k, dhi, idesc, 1u);
-            }
-          }
+        // one straight-line body per chunk kind (the generic loop with its per-MMA predication costs the single
+        // issue thread ~2x the instructions of the common single-tap case)
+        const uint32_t kind = (cur >> 2) & 7u;                                 // g | both << 2
+        if (kind == 1u) {
+          issue_mmas<BN, BK, THREE, 1, false>(d_main, da_hi0, da_lo0, db00, 0u, started);
+        } else if (kind == 3u) {
+          issue_mmas<BN, BK, THREE, 3, false>(d_main, da_hi0, da_lo0, db00, cur >> 5, started);
+        } else if (kind == 2u) {
+          issue_mmas<BN, BK, THREE, 2, false>(d_main, da_hi0, da_lo0, db00, cur >> 5, started);
+        } else {
+          issue_mmas<BN, BK, THREE, 1, true>(d_main, da_hi0, da_lo0, db00, 0u, started);
         }
+        started = 1;
         umma_commit(empty_bar + s);              // frees the smem slot once these MMAs have read it
         if (close_seg) { umma_commit(seg_full_bar + buf); ++g; }
         if (++s == stages) { s = 0; ph ^= 1; }
