@@ -636,10 +636,16 @@ struct Builder {
       }
       if (!rc) rc = make_map2(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
       if (!rc) rc = make_map2(&tp.b_lo, W.lo, W.K, N, bk, bn, bk == 64);
-      // accumulation segments (see gemm_tc.cu): 16 truncating MMAs per chain, then promotion to registers
+      // accumulation segments (see gemm_tc.cu): a bounded chain of truncating MMAs, then promotion to registers
       tp.tile_chunks = 0;
       for (auto& t : taps) tp.tile_chunks += t.nch / bk;           // ring slots (group chunks) per tile
-      tp.seg_chunks = std::max(1, 16 / ((bk / 16) * gmax));
+      // K steps per truncating accumulation chain.  Longer chains = fewer promotion drains and a longer run-ahead of
+      // the MMA thread while the epilogue warps are in their output phase (two TMEM buffers = two segments), but
+      // more truncation drift.  Measured on the T = 1001 golden (max log-mel error, UNet ms): 16: 3.1e-5, 33.8;
+      // 24: 3.8e-5, 32.0; 32: 4.1e-5, 31.0; 48: 5.5e-5, 30.1 (bar 1e-4).
+      int seg_mmas = 24;
+      if (const char* ov = getenv("VF_TUNE_SEG_MMAS")) seg_mmas = std::max(4, atoi(ov));
+      tp.seg_chunks = std::max(1, seg_mmas / ((bk / 16) * gmax));
       tp.a_box_rows = a_box_rows;
       tp.gmax = gmax;
       bool any_both = false;

@@ -11,7 +11,7 @@
 //
 // Accumulation precision.  The tensor core adds into its fp32 accumulator with truncation, so one long chain
 // of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with one accumulator per
-// tile).  In 3-term mode the K loop is therefore cut into segments of 16 MMAs that ping-pong between two TMEM
+// tile).  In 3-term mode the K loop is therefore cut into segments of 24 K steps that ping-pong between two TMEM
 // accumulator buffers; the epilogue warps add each finished segment into registers in fp32 round-to-nearest
 // ("promotion") while the tensor core already works on the next one.  Each buffer is [main | correction]: the
 // two small correction products (hi*lo, lo*hi) never mix into the main chain.  The same ping-pong is the tile double buffering
