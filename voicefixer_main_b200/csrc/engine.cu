@@ -663,7 +663,13 @@ struct Builder {
       }
       int stages = 0;
       for (; ctas >= 1; --ctas) {
-        tp.tmem_cols = pow2((terms == 3 ? 4 : 2) * bn);
+        // accumulator buffers: four where TMEM allows (run-ahead of the MMA thread over the epilogue's output phase)
+        const int acc_w = (terms == 3 ? 2 : 1) * bn;
+        int nb_log = 1;
+        if (pow2(4 * acc_w) * ctas <= 512) nb_log = 2;
+        if (const char* ov = getenv("VF_TUNE_NBUF")) { if (atoi(ov) == 2) nb_log = 1; }
+        tp.nbuf_log = nb_log;
+        tp.tmem_cols = pow2((1 << nb_log) * acc_w);
         if (tp.tmem_cols * ctas > 512) continue;
         const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
         for (stages = 8; stages >= 2; --stages)

@@ -101,7 +101,8 @@ struct GemmTcParams {
   int stages;
   int tile_chunks; // BK-wide K chunks per output tile
   int seg_chunks;  // 3-term mode: chunks per accumulation segment (promotion to registers in between)
-  int tmem_cols;   // power of two >= 2 * BN (main ping-pong) [+ 2 * BN correction accumulators in 3-term mode]
+  int tmem_cols;   // power of two >= (1 << nbuf_log) accumulator buffers of BN (1-term) or 2 * BN (3-term: [main | correction]) columns
+  int nbuf_log;    // log2 of the number of accumulator buffers rotating in TMEM (1 or 2)
   int planes_a;    // smem slots per stage for A: 2 when any tap contracts the lo plane
   int a_box_rows;  // rows per A TMA box: 128, or 130 when taps are grouped (halo)
   int gmax;        // largest tap group: B slots per stage

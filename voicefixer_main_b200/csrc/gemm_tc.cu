@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
   uint8_t* tail = stg_base + EPI_WARPS * 4096;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* seg_full_bar = empty_bar + stages;           // [2] main accumulator buffer holds a finished segment
-  uint64_t* seg_empty_bar = seg_full_bar + 2;            // [2] ... has been drained by every epilogue thread
+  uint64_t* seg_full_bar = empty_bar + stages;           // [nbuf <= 4] accumulator buffer holds a finished segment
+  uint64_t* seg_empty_bar = seg_full_bar + 4;            // [nbuf <= 4] ... has been drained by every epilogue thread
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(seg_empty_bar + 4);   // keep the float arrays 16-byte aligned
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
   const int total_tiles = pr.n_img * pr.m_tiles * n_tiles;
   const int tile_chunks = P.tile_chunks;                 // K chunks per tile
   const int seg_chunks = THREE ? P.seg_chunks : tile_chunks;   // K chunks per accumulation segment
-  // TMEM columns: accumulator buffers ping-pong.  1-term: M0 [0,BN) M1 [BN,2BN).  3-term: [M0|C0] [M1|C1], each
+  const int nbuf_log = P.nbuf_log, nbuf_mask = (1 << nbuf_log) - 1;   // 2 or 4 accumulator buffers rotate in TMEM
+  // TMEM columns: 2 or 4 accumulator buffers rotate (as many as 512 columns / co-resident CTAs allow: the MMA
+  // thread can run that many segments ahead of the epilogue warps).  1-term: M0 [0,BN) M1 [BN,2BN) ...  3-term: [M0|C0] [M1|C1] ..., each
   // 2*BN wide: hi*hi and hi*lo come from ONE MMA of width 2*BN against the stacked [B_hi; B_lo] tile (A_hi is read
   // from shared memory once instead of twice), lo*hi is a second MMA of width BN into the C half.
 
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i <= nbuf_mask; ++i) {
       mbar_init(seg_full_bar + i, 1);
       mbar_init(seg_empty_bar + i, EPI_THREADS);
     }
@@ -257,8 +259,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         fl = s_tab[ci + 1 < tile_chunks ? ci + 1 : 0].flags;
         if (left_in_seg == 0) {                // open a segment: its accumulator buffer must have been drained
           left_in_seg = min(seg_chunks, tile_chunks - ci);
-          buf = g & 1;
-          if (!mbar_wait(seg_empty_bar + buf, ((g >> 1) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+          buf = g & nbuf_mask;
+          if (!mbar_wait(seg_empty_bar + buf, ((g >> nbuf_log) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
           d_main = tmem_base + buf * ACC_W;
           started = 0;
         }
@@ -582,8 +584,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         // truncating tensor-core adds is longer than one segment; the small hi*lo + lo*hi sums join at the end.
         float acc[NJ][32];
         for (int sg = 0; sg < nseg && ok; ++sg, ++g) {
-          const int buf = g & 1;
-          if (!mbar_wait(seg_full_bar + buf, (g >> 1) & 1, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+          const int buf = g & nbuf_mask;
+          if (!mbar_wait(seg_full_bar + buf, (g >> nbuf_log) & 1, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
           tc_fence_after();
 #pragma unroll
           for (int jj = 0; jj < NJ; ++jj) {
@@ -612,8 +614,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
         }
       } else {
-        const int buf = g & 1;
-        if (!mbar_wait(seg_full_bar + buf, (g >> 1) & 1, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+        const int buf = g & nbuf_mask;
+        if (!mbar_wait(seg_full_bar + buf, (g >> nbuf_log) & 1, e.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
         tc_fence_after();
 #pragma unroll 1
         for (int j = half; j < BN / 32; j += CHUNK_STEP) {
@@ -647,7 +649,7 @@ size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, i
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
   const size_t stage = planes_a * a_slot + (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2;
   const int ew = epi_warps_for(bn, terms);
-  return stages * stage + ew * 4096 + (2 * stages + 6) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + (size_t)tile_chunks * 16 + 1024;
+  return stages * stage + ew * 4096 + (2 * stages + 8) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + (size_t)tile_chunks * 16 + 1024;
 }
 
 template <int BN, int BK, int EW, bool THREE, int MINB>
