@@ -253,11 +253,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       uint32_t d_main = 0, started = 0;
       int left_in_seg = 0, buf = 0;                      // countdown: no division on the issue path
+      if (!THREE) {                                      // hi-only: one segment per tile, opened here, closed after the loop
+        buf = g & nbuf_mask;
+        if (!mbar_wait(seg_empty_bar + buf, ((g >> nbuf_log) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
+        d_main = tmem_base + buf * ACC_W;
+      }
       uint32_t fl = s_tab[0].flags;
       for (int ci = 0; ci < tile_chunks; ++ci) {
         const uint32_t cur = fl;
         fl = s_tab[ci + 1 < tile_chunks ? ci + 1 : 0].flags;
-        if (left_in_seg == 0) {                // open a segment: its accumulator buffer must have been drained
+        if (THREE && left_in_seg == 0) {       // open a segment: its accumulator buffer must have been drained
           left_in_seg = min(seg_chunks, tile_chunks - ci);
           buf = g & nbuf_mask;
           if (!mbar_wait(seg_empty_bar + buf, ((g >> nbuf_log) & 1) ^ 1, e.err, ERR_PIPE_MMA)) { ok = false; break; }
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         }
         if (!mbar_wait(full_bar + s, ph, e.err, ERR_PIPE_MMA)) { ok = false; break; }
         tc_fence_after();
-        const bool close_seg = --left_in_seg == 0;
+        const bool close_seg = THREE ? (--left_in_seg == 0) : (ci + 1 == tile_chunks);
         // descriptors differ only in the 14-bit start-address field of their low word (units of 16 B): +2 per
         // 32-byte K step, +ROW_BYTES/16 per row of halo shift, +B_SLOT/16 per weight tile of a tap group
         const uint32_t da_hi0 = make_smem_desc_lo(smem_u32(smem + (size_t)s * stage_bytes));
