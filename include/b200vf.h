@@ -15,6 +15,7 @@
  *   vf_restore / vf_restore_host  one iteration of the segment loop of handler(), eval_gsr_voicefixer.py:49-74:
  *                                 pre -> model -> from_log -> vocoder -> peak normalise -> trim_center
  *   vf_to_log / vf_from_log       tools/pytorch/pytorch_util.py:157-163
+ *   vf_to_pcm16                   the int16 conversion of save_wave, tools/file/wav.py:22-24
  *
  * Conventions: every function returns 0 on success or a negative VF_E* code and never throws; the message is
  * available from vf_last_error().  All tensor arguments are contiguous fp32.  Unless a name ends in `_host`,
@@ -118,6 +119,10 @@ VF_API int vf_restore_stages(vf_ctx* ctx, int batch, int64_t n_samples, float* m
 
 VF_API int vf_to_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream);
 VF_API int vf_from_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream);
+/* fp32 samples -> 16-bit PCM exactly as save_wave does it: x * 2^15, truncation toward zero through a 32-bit integer,
+ * low 16 bits kept (so +1.0 wraps to -32768 like numpy's astype(np.short) on the reference's hosts).  `out` is a
+ * device buffer of n int16. */
+VF_API int vf_to_pcm16(vf_ctx* ctx, const float* in, int16_t* out, int64_t n, void* stream);
 
 /* Device memory the plan for (batch, n_samples) holds (activations + packed weights). */
 VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n_samples, size_t* bytes);

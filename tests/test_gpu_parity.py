@@ -269,3 +269,49 @@ def test_host_entry_point_and_launch_count(model):
     assert eng.launch_count() - n0 > 100          # our kernels ran, not a library fallback
     assert torch.equal(pin_out, dev)
     assert eng.workspace_bytes(2, 8820) > 0
+
+
+def test_pcm16_matches_save_wave_cast(model):
+    """the int16 conversion of tools/file/wav.py:22-24 on the GPU, bit for bit."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(3, 70001, generator=g) * 2 - 1
+    x = x * (x.abs() < 0.99997)                                    # keep |x * 2^15| < 32767 in the random part
+    edge = torch.tensor([0.0, 1e-6, -1e-6, 0.5, -0.5, 1 - 2.0 ** -15, -(1 - 2.0 ** -15), 32767.5 / 32768, -32767.5 / 32768,
+                         -1.0, 3.0517578125e-05, -3.0517578125e-05, 4.57763671875e-05, -4.57763671875e-05])
+    x[0, :edge.numel()] = edge
+    def expect(v):      # x * 2^15, truncate toward zero through a wide integer, keep the low 16 bits
+        t = np.trunc(v.astype(np.float32) * np.float32(32768)).astype(np.int64)
+        return (t & 0xffff).astype(np.uint16).view(np.int16)
+
+    got = model._engine().to_pcm16(x.cuda()).cpu().numpy()
+    assert got.dtype == np.int16 and got.shape == (3, 70001)
+    assert np.array_equal(got, O.to_int16(x.numpy()))              # in range: numpy's own truncating cast
+    assert np.array_equal(got, expect(x.numpy()))
+    # +1.0 (a peak-normalised maximum) overflows: x86 numpy goes through int32 and keeps the low 16 bits
+    one = model._engine().to_pcm16(torch.ones(4, device="cuda")).cpu().numpy()
+    assert np.array_equal(one, np.full(4, -32768, dtype=np.int16))
+    wav = O.synth_clips(2, 8820, seed=4).cuda()
+    pcm = model.restore_pcm16(wav)
+    assert pcm.dtype == torch.int16 and pcm.shape == (2, 8820)
+    assert np.array_equal(pcm.cpu().numpy(), expect(model.restore(wav).cpu().numpy()))
+
+
+def test_longform_margins_vs_oracle(model, state):
+    """boxcar overlap-add with context margins (tools/dsp/overlapadd_boxcar.py:416-518) over
+    the engine, middle chunks batched, against the same schedule over the oracle."""
+    from voicefixer_main_b200.longform import BoxcarOverlapAdd, RestoreNet, restore_longform
+    W, M = 22050, 4410
+    n = 3 * W + 8837                                               # 4 chunks, ragged tail
+    wav = O.synth_clips(2, n, seed=41)
+
+    class OracleNet:
+        def __call__(self, x):
+            with torch.no_grad():
+                return {"wav": O.restore(state, x[:, 0, :], exact_stft=True)[:, None, :]}
+
+    ours = BoxcarOverlapAdd(RestoreNet(model), 1, W, M)(wav.cuda()[:, None, :])[:, 0].cpu()
+    ref = BoxcarOverlapAdd(OracleNet(), 1, W, M)(wav[:, None, :])[:, 0]
+    assert ours.shape == ref.shape == (2, n)
+    assert float((ours - ref).pow(2).mean().sqrt()) < WAV_RMS_TOL
+    again = restore_longform(model, wav.cuda(), window_size=W, in_margin=M).cpu()
+    assert torch.equal(again, ours)

@@ -16,7 +16,7 @@ VF_OK, VF_EINVAL, VF_ENODEVICE, VF_ECUDA, VF_ESTATE, VF_EDEVICE, VF_EASSERT = 0,
 EXPORTS = [
     "vf_default_config", "vf_create", "vf_destroy", "vf_last_error", "vf_load_weights", "vf_frontend",
     "vf_unet_mel", "vf_vocoder", "vf_vocoder_out_len", "vf_restore", "vf_restore_host", "vf_restore_stages",
-    "vf_to_log", "vf_from_log", "vf_workspace_bytes", "vf_check_errors", "vf_set_option", "vf_launch_count",
+    "vf_to_log", "vf_from_log", "vf_to_pcm16", "vf_workspace_bytes", "vf_check_errors", "vf_set_option", "vf_launch_count",
     "vf_enable_stage_timing", "vf_stage_times", "vf_selftest_gemm", "vf_enable_op_timing", "vf_op_count", "vf_op_info",
 ]
 
@@ -74,6 +74,7 @@ def load_library():
     lib.vf_restore_stages.argtypes = [P, c_int, c_int64, P, P, P]
     lib.vf_to_log.argtypes = [P, P, P, c_int64, P]
     lib.vf_from_log.argtypes = [P, P, P, c_int64, P]
+    lib.vf_to_pcm16.argtypes = [P, P, P, c_int64, P]
     lib.vf_workspace_bytes.argtypes = [P, c_int, c_int64, POINTER(c_size_t)]
     lib.vf_check_errors.argtypes = [P, P]
     lib.vf_set_option.argtypes = [P, c_char_p, c_int]

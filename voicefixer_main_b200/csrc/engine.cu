@@ -1363,6 +1363,14 @@ VF_API int vf_from_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void
   return VF_OK;
 }
 
+VF_API int vf_to_pcm16(vf_ctx* ctx, const float* in, int16_t* out, int64_t n, void* stream) {
+  if (!ctx || !in || !out || n <= 0) return VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_pcm16(in, out, (size_t)n, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+
 VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n, size_t* bytes) {
   int rc = check_ready(ctx);
   if (rc) return rc;

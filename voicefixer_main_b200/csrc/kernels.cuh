@@ -108,5 +108,6 @@ struct FinalizeParams {
   long out_ld, out_off;
 };
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream);
+cudaError_t launch_pcm16(const float* in, int16_t* out, size_t n, cudaStream_t stream);
 
 }  // namespace vf

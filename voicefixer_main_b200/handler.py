@@ -42,6 +42,15 @@ def save_wave(frames: np.ndarray, fname, sample_rate=44100):
         w.writeframes(pcm.tobytes())
 
 
+def save_pcm16(pcm: np.ndarray, fname, sample_rate=44100):
+    """Write already-converted int16 samples (VoiceFixer.restore_pcm16 / Engine.to_pcm16)."""
+    with wave.open(fname, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(sample_rate)
+        w.writeframes(np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1).tobytes())
+
+
 def refresh_model(ckpt):
     global model
     model = VoiceFixer(hp if hp is not None else default_hparams(), channels=2, type_target="vocals").load_from_checkpoint(ckpt)
@@ -69,5 +78,7 @@ def handler(input, output, target, ckpt, device, needrefresh=False, meta={}):
     metrics = {}
     wav_10k = load_wav(input, sample_rate=44100)
     out = restore_array(model, wav_10k, model.device, unify_energy=bool(meta.get("unify_energy", False)))
-    save_wave(out[0].detach().cpu().numpy(), fname=output, sample_rate=44100)
+    # save_wave's float -> int16 conversion runs on the GPU (its `max <= 1` condition always holds after the
+    # per-segment peak normalisation), so only 2 bytes per sample cross PCIe
+    save_pcm16(model._engine().to_pcm16(out[0]).cpu().numpy(), fname=output, sample_rate=44100)
     return metrics

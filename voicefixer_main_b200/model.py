@@ -240,6 +240,14 @@ class Engine:
             self._ck(self.lib.vf_from_log(self.ctx, _ptr(x), _ptr(out), x.numel(), _stream()))
         return out
 
+    def to_pcm16(self, x):
+        """fp32 samples -> int16 PCM exactly as save_wave (tools/file/wav.py:22-24) converts them."""
+        x = _check_in(x, self.device, "input")
+        out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_to_pcm16(self.ctx, _ptr(x), _ptr(out), x.numel(), _stream()))
+        return out
+
     def check_errors(self):
         """Synchronises the current stream and raises on sticky device errors (AssertionError for the
         to_log negative-input assertion, as tools/pytorch/pytorch_util.py:158 does)."""
@@ -489,3 +497,8 @@ class VoiceFixer:
 
     def restore_host(self, wav_host: torch.Tensor, out_host: torch.Tensor):
         self._engine().restore_host(wav_host, out_host)
+
+    def restore_pcm16(self, wav: torch.Tensor, unify_energy: bool = False) -> torch.Tensor:
+        """restore() followed by the on-GPU int16 conversion of save_wave (tools/file/wav.py:22-24): [B,N] int16,
+        half the device-to-host bytes of the fp32 result."""
+        return self._engine().to_pcm16(self.restore(wav, unify_energy=unify_energy))
