@@ -56,6 +56,7 @@ struct Planes {
   PlanePtr p{nullptr, nullptr};
   int C = 0;
   int img_rows = 0;   // allocated rows per image
+  size_t plane_stride = 0;   // elements from the hi plane to the lo plane (same allocation)
 };
 struct ASrc {
   Planes pl;
@@ -214,10 +215,10 @@ int upload_gemm(vf_ctx* ctx, GemmW* w, const std::vector<float>& m, int N, int K
   }
   w->N = N;
   w->K = K;
+  hi.insert(hi.end(), lo.begin(), lo.end());     // [hi matrix][lo matrix]: one 3-D TMA box fetches a tile of both
   int rc = upload(ctx, &w->hi, hi);
   if (rc) return rc;
-  rc = upload(ctx, &w->lo, lo);
-  if (rc) return rc;
+  w->lo = w->hi + m.size();
   if (bias) return upload(ctx, &w->bias, *bias);
   return VF_OK;
 }
@@ -472,8 +473,9 @@ struct Builder {
     pl.C = C;
     pl.img_rows = img_rows;
     const size_t cnt = n_img * (size_t)img_rows * C;
-    pl.p.hi = alloc<__half>(cnt);
-    pl.p.lo = alloc<__half>(cnt);
+    pl.p.hi = alloc<__half>(2 * cnt);        // [hi plane][lo plane]: one 4-D TMA box fetches both (3-term GEMMs)
+    pl.p.lo = pl.p.hi ? pl.p.hi + cnt : nullptr;
+    pl.plane_stride = cnt;
     return pl;
   }
 
@@ -486,6 +488,29 @@ struct Builder {
                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(A: C=%d rows=%d img_rows=%d n=%d box=%d) -> %d", C, rows, img_rows, n_img, box_c, (int)r);
+    return VF_OK;
+  }
+  // 3-term operands: hi and lo planes in ONE box ([C, rows, image, plane] / [K, N, plane]) - half the TMA issues
+  int make_map4(CUtensorMap* m, const __half* base, int C, int rows, int img_rows, int n_img, size_t plane_stride, int box_c, bool sw128, int box_rows) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_img, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)img_rows * C * 2, (cuuint64_t)plane_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1, 2};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(A hi+lo: C=%d rows=%d img_rows=%d n=%d box=%dx%d) -> %d", C, rows, img_rows, n_img, box_c, box_rows, (int)r);
+    return VF_OK;
+  }
+  int make_map3w(CUtensorMap* m, const __half* base, int K, int N, int box_k, int box_n, bool sw128) {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_n, 2};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(B hi+lo: K=%d N=%d box=%dx%d) -> %d", K, N, box_k, box_n, (int)r);
     return VF_OK;
   }
   int make_map2(CUtensorMap* m, const __half* base, int K, int N, int box_k, int box_n, bool sw128) {
@@ -595,7 +620,9 @@ struct Builder {
         }
       }
     }
-    const int a_box_rows = gmax > 1 ? GEMM_BM + 2 : GEMM_BM;
+    // halo boxes: 128 + 2 rows; 3-term GEMMs fetch the hi and lo planes in one 4-D box, whose planes land back to
+    // back in shared memory, so the box is grown to a whole number of 1024-byte swizzle atoms (136 / 144 rows)
+    const int a_box_rows = gmax > 1 ? (terms == 3 ? (bk == 64 ? 136 : 144) : GEMM_BM + 2) : GEMM_BM;
     if (k != W.K) { rc = fail(ctx, VF_EINVAL, "GEMM K mismatch: taps cover %d, packed weight has %d", k, W.K); return; }
     GemmProblem pr;
     memset(&pr, 0, sizeof pr);
@@ -631,11 +658,20 @@ struct Builder {
       const ASrc* srcs[2] = {&s0, s1 ? s1 : &s0};
       for (int i = 0; i < 2 && !rc; ++i) {
         const size_t off = (size_t)srcs[i]->row0 * srcs[i]->pl.C;
-        rc = make_map3(&tp.a_hi[i], srcs[i]->pl.p.hi + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64, a_box_rows);
-        if (!rc) rc = make_map3(&tp.a_lo[i], srcs[i]->pl.p.lo + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64, a_box_rows);
+        if (terms == 3) {
+          if (srcs[i]->pl.plane_stride == 0) rc = fail(ctx, VF_EINVAL, "3-term GEMM source without adjacent hi/lo planes");
+          if (!rc) rc = make_map4(&tp.a_hi[i], srcs[i]->pl.p.hi + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, srcs[i]->pl.plane_stride, bk, bk == 64, a_box_rows);
+        } else {
+          rc = make_map3(&tp.a_hi[i], srcs[i]->pl.p.hi + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64, a_box_rows);
+          if (!rc) rc = make_map3(&tp.a_lo[i], srcs[i]->pl.p.lo + off, srcs[i]->pl.C, srcs[i]->rows, srcs[i]->pl.img_rows, n_img, bk, bk == 64, a_box_rows);
+        }
       }
-      if (!rc) rc = make_map2(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
-      if (!rc) rc = make_map2(&tp.b_lo, W.lo, W.K, N, bk, bn, bk == 64);
+      if (terms == 3) {
+        if (!rc) rc = make_map3w(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
+      } else {
+        if (!rc) rc = make_map2(&tp.b_hi, W.hi, W.K, N, bk, bn, bk == 64);
+        if (!rc) rc = make_map2(&tp.b_lo, W.lo, W.K, N, bk, bn, bk == 64);
+      }
       // accumulation segments (see gemm_tc.cu): a bounded chain of truncating MMAs, then promotion to registers
       tp.tile_chunks = 0;
       for (auto& t : taps) tp.tile_chunks += t.nch / bk;           // ring slots (group chunks) per tile

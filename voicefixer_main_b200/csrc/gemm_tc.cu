@@ -101,7 +101,10 @@ __device__ __forceinline__ void issue_mmas(uint32_t d_main, uint32_t da_hi0, uin
   constexpr uint32_t dhi = make_smem_desc_hi(BK * 2);
   constexpr uint32_t ROW_UNITS = BK * 2 / 16;
   constexpr uint32_t B_SLOT_UNITS = (THREE ? 2 : 1) * BN * BK * 2 / 16;
-#pragma unroll 1
+  // the tap loop is unrolled where the kernel's register budget has room (narrow tiles): every rolled iteration costs
+  // the single issue thread ~25 instructions of loop and shift bookkeeping per 2-4 MMAs
+  constexpr int UNROLL_G = BN <= 64 ? G : 1;
+#pragma unroll UNROLL_G
   for (int gi = 0; gi < G; ++gi) {
     const uint32_t sh = G == 1 ? 0u : ((shifts >> (2 * gi)) & 3u) * ROW_UNITS;
     const uint32_t db0 = db00 + gi * B_SLOT_UNITS;
@@ -176,10 +179,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
     tma_prefetch_desc(&P.b_hi);
-    if (THREE) {
-      tma_prefetch_desc(&P.a_lo[0]);
-      tma_prefetch_desc(&P.b_lo);
-    }
+    if (!THREE) tma_prefetch_desc(&P.a_lo[0]);
   }
   if (warp == 1) tmem_alloc_dyn(tmem_holder, P.tmem_cols);
   for (int ci = threadIdx.x; ci < tile_chunks; ci += blockDim.x) {   // flatten taps x K chunks (see ChunkDesc)
@@ -230,13 +230,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         const int tg = (cur.flags >> 2) & 3u;
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_expect_tx(full_bar + s, (a_lo ? 2u : 1u) * a_box_bytes + tg * B_SLOT);
-        tma_load_3d(st, &P.a_hi[src], full_bar + s, cur.a_c, m0 + cur.a_off, img);
-        if (a_lo) tma_load_3d(st + a_slot, &P.a_lo[src], full_bar + s, cur.a_c, m0 + cur.a_off, img);
         const int k0 = cur.kk & 0xffffu, ks = cur.kk >> 16;
-        for (int gi = 0; gi < tg; ++gi) {
-          uint8_t* sb = st + off_b + gi * B_SLOT;
-          tma_load_2d(sb, &P.b_hi, full_bar + s, k0 + gi * ks, n0);
-          if (THREE) tma_load_2d(sb + B_BYTES, &P.b_lo, full_bar + s, k0 + gi * ks, n0);
+        if (THREE) {      // hi and lo planes of A in one 4-D box, [B_hi][B_lo] of a tap in one 3-D box (a_slot == box bytes)
+          tma_load_4d(st, &P.a_hi[src], full_bar + s, cur.a_c, m0 + cur.a_off, img, 0);
+          for (int gi = 0; gi < tg; ++gi) tma_load_3d(st + off_b + gi * B_SLOT, &P.b_hi, full_bar + s, k0 + gi * ks, n0, 0);
+        } else {
+          tma_load_3d(st, &P.a_hi[src], full_bar + s, cur.a_c, m0 + cur.a_off, img);
+          if (a_lo) tma_load_3d(st + a_slot, &P.a_lo[src], full_bar + s, cur.a_c, m0 + cur.a_off, img);
+          for (int gi = 0; gi < tg; ++gi) tma_load_2d(st + off_b + gi * B_SLOT, &P.b_hi, full_bar + s, k0 + gi * ks, n0);
         }
         if (++s == stages) { s = 0; ph ^= 1; }
       }
