@@ -66,5 +66,28 @@ def main():
     print("golden written to", GOLD)
 
 
+def main_ssr():
+    """SURVEY.md 8(f) row 1 (next path): models/components/unet_v2.py UNetResComplex_100Mb imported unmodified, with
+    the UNet tensors of make_state(SEED) under the SSR prefix (same shapes, models/ssr_unet.py:49).  Its STFT/ISTFT
+    helpers are the oracle's restatements (torchlibrosa is absent)."""
+    from voicefixer_main_b200.arch import UNET_PREFIX
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_state(SEED)
+    ssr = {k.replace(UNET_PREFIX, "generator.unet."): v for k, v in sd.items() if k.startswith(UNET_PREFIX)}
+    net = ref_import.build_reference_unet_v2(ssr)
+    fp = state_fingerprint(sd)
+    with torch.no_grad():
+        wav = O.synth_clips(2, 63 * 441 + 200, seed=51)[:, None, :]     # T = 64 frames, ragged sample count
+        sp, cos, sin = net.f_helper.wav_to_spectrogram_phase(wav)
+        out = net(sp, wav)["wav"]
+        mag = O.unet_v2_forward(ssr, sp)                                  # bit-identical to the module's out_mag (tested)
+    np.savez_compressed(os.path.join(GOLD, "ssr_t64.npz"), wav=wav[:, 0].numpy(), out_mag=mag.numpy(),
+                        out=out[:, 0].numpy(), fingerprint=fp)
+    print("ssr_t64 out rms", float(out.pow(2).mean().sqrt()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ssr":
+        main_ssr()
+    else:
+        main()

@@ -89,15 +89,23 @@ def install_shims():
         def __init__(self, n_fft=2048, hop_length=None, win_length=None, window="hann", center=True,
                      pad_mode="reflect", freeze_parameters=True):
             super().__init__()
-            assert (n_fft, hop_length, win_length, window, center, pad_mode) == \
+            # unet_v2.py:29 passes center=(True,) (a stray comma): truthy, which is all torchlibrosa tests
+            assert (n_fft, hop_length, win_length, window, bool(center), pad_mode) == \
                 (vf_oracle.N_FFT, vf_oracle.HOP, vf_oracle.N_FFT, "hann", True, "reflect")
 
         def forward(self, x):
             return vf_oracle.stft_conv_dft(x)
 
     class ISTFT(nn.Module):
-        def __init__(self, **kw):
+        """torchlibrosa.stft.ISTFT stand-in: oracle.vf_oracle.istft (restated, pinned by torch.istft / round trip)."""
+
+        def __init__(self, n_fft=2048, hop_length=None, win_length=None, window="hann", center=True,
+                     pad_mode="reflect", freeze_parameters=True, **kw):
             super().__init__()
+            assert (n_fft, hop_length, win_length, window, bool(center)) == (vf_oracle.N_FFT, vf_oracle.HOP, vf_oracle.N_FFT, "hann", True)
+
+        def forward(self, real_stft, imag_stft, length):
+            return vf_oracle.istft(real_stft, imag_stft, length)
 
     sys.modules["torchlibrosa.stft"].STFT = STFT
     sys.modules["torchlibrosa.stft"].ISTFT = ISTFT
@@ -145,6 +153,26 @@ def build_reference_model(state: dict, config: str = "config/vctk_base_voicefixe
     model.vocoder.set_state({k: v for k, v in state.items() if k.startswith("vocoder.")})
     model.eval()
     return model, hp
+
+
+def build_reference_unet_v2(state: dict, prefix: str = "generator.unet."):
+    """The reference's SSR analysis network (models/components/unet_v2.py:20, channels=1) in eval mode with the
+    tensors of `state` under `prefix` loaded; its STFT/ISTFT helpers are the shims above."""
+    install_shims()
+    cwd = os.getcwd()
+    os.chdir(REPO_ROOT)
+    try:
+        from models.components.unet_v2 import UNetResComplex_100Mb
+        net = UNetResComplex_100Mb(channels=1)
+    finally:
+        os.chdir(cwd)
+    own = net.state_dict()
+    sd = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix) and k[len(prefix):] in own}
+    missing = [k for k in own if k not in sd and not k.startswith("f_helper.")]
+    assert not missing, missing[:5]
+    net.load_state_dict(sd, strict=False)
+    net.eval()
+    return net
 
 
 def reference_handler_batch(model, wav: torch.Tensor, seg_samples: int = 44100 * 60, collect=None):

@@ -192,6 +192,66 @@ def unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = UNE
     return x[:, :, 0:origin_len, :]
 
 
+def unet_v2_forward(sd: Dict[str, torch.Tensor], sp: torch.Tensor, prefix: str = "generator.unet.") -> torch.Tensor:
+    """SURVEY.md 8(f) row 1 (next path, BASELINE config 3): the magnitude branch of
+    models/components/unet_v2.py:86-132.  sp [B,1,T,1025] linear magnitude -> out_mag [B,1,T,1025].
+    Same blocks as unet_forward, but on F = 1024 bins, the decoders prune BOTH the last time row and the last
+    frequency column (`both=True`, modules.py:203-210) and the output is used as the magnitude itself (:134-136)."""
+    sd = {k[len(prefix):]: v.to(sp.dtype) if v.is_floating_point() else v
+          for k, v in sd.items() if k.startswith(prefix)}
+    x = sp
+    origin_len = x.shape[2]
+    x = F.pad(x, (0, 0, 0, padded_frames(origin_len) - origin_len))    # unet_v2.py:101-104
+    x = x[..., 0:x.shape[-1] - 1]                                       # unet_v2.py:108
+    skips = []
+    for i in range(1, len(ENC_CHANNELS) + 1):
+        for j in range(1, 5):
+            x = _conv_block_res(x, sd, f"encoder_block{i}.conv_block{j}")
+        skips.append(x)
+        x = F.avg_pool2d(x, kernel_size=(2, 2))
+    x = _conv_block_res(x, sd, "conv_block7")
+    for i in range(1, len(DEC_CHANNELS) + 1):
+        p = f"decoder_block{i}"
+        x = F.conv_transpose2d(F.relu(_bn(x, sd, p + ".bn1")), sd[p + ".conv1.weight"], stride=2)
+        x = x[:, :, 0:-1, 0:-1]                                         # prune, both=True (modules.py:207-208)
+        x = torch.cat((x, skips[-i]), dim=1)
+        for j in range(2, 6):
+            x = _conv_block_res(x, sd, f"{p}.conv_block{j}")
+    x = _conv_block_res(x, sd, "after_conv_block1")
+    x = F.conv2d(x, sd["after_conv2.weight"], sd["after_conv2.bias"])
+    x = F.pad(x, (0, 1))                                                # unet_v2.py:128
+    return x[:, :, 0:origin_len, :][:, 0:1]                             # unet_v2.py:129-131
+
+
+def istft(real: torch.Tensor, imag: torch.Tensor, length: int) -> torch.Tensor:
+    """FDomainHelper.istft (fDomainHelper.py:30-32, 127) = torchlibrosa 0.0.7 ISTFT.forward with n_fft = win = 2048,
+    hop = 441, periodic hann, center=True.  The package is absent from this image: restated from its published
+    algorithm [recollection] - mirror the half spectrum, inverse DFT of every frame, multiply by the window,
+    overlap-add, divide by the overlap-added squared window (clamped at 1e-11), drop n_fft/2 samples and keep
+    `length`.  PINNED ONLY BY PROPERTY: tests check it against torch.istft (same definition) and the
+    stft -> istft round trip.  real, imag [B,1,T,1025] -> [B,length]."""
+    spec = torch.complex(real[:, 0].double(), imag[:, 0].double())       # [B,T,1025]
+    frames = torch.fft.irfft(spec, n=N_FFT, dim=-1)                      # = Re(idft of the mirrored full spectrum) / n_fft
+    win = hann_periodic()
+    frames = frames * win
+    b, t, _ = frames.shape
+    out_len = (t - 1) * HOP + N_FFT
+    y = F.fold(frames.transpose(1, 2), output_size=(1, out_len), kernel_size=(1, N_FFT), stride=(1, HOP))[:, 0, 0, :]
+    wsum = F.fold((win ** 2)[None, :, None].repeat(1, 1, t), output_size=(1, out_len), kernel_size=(1, N_FFT),
+                  stride=(1, HOP))[0, 0, 0, :]
+    y = y / torch.clamp(wsum, 1e-11, np.inf)
+    return y[:, N_FFT // 2:N_FFT // 2 + length].to(real.dtype)
+
+
+def ssr_forward(sd, wav: torch.Tensor, exact_stft: bool = False) -> torch.Tensor:
+    """SSR_UNet.forward (models/ssr_unet.py:144-155) after pre (:140-143): wav [B,1,N] -> restored wav [B,1,N]:
+    magnitude from the UNet, phase of the input (unet_v2.py:97,138-139), ISTFT to the input length (:141-143)."""
+    sp, cos_in, sin_in = wav_to_spectrogram_phase(wav, exact=exact_stft)
+    out_mag = unet_v2_forward(sd, sp.float())
+    y = istft(out_mag * cos_in.float(), out_mag * sin_in.float(), wav.shape[2])
+    return y[:, None, :]
+
+
 def generator_forward(sd, mel_orig: torch.Tensor) -> torch.Tensor:
     """Generator.forward (gsr_voicefixer.py:86-91): returns the log10 mel."""
     logm = to_log(mel_orig)

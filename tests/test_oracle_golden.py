@@ -52,3 +52,42 @@ def test_segment_loop_and_trim():
     x = torch.tensor([[[0.5, -2.0]], [[0.25, 0.5]]])
     y = O.peak_normalize(x)
     assert y[0].tolist() == [[0.25, -1.0]] and torch.equal(y[1], x[1])
+
+
+def _ssr_state(state):
+    from voicefixer_main_b200.arch import UNET_PREFIX
+    return {k.replace(UNET_PREFIX, "generator.unet."): v for k, v in state.items() if k.startswith(UNET_PREFIX)}
+
+
+def test_istft_restatement_properties():
+    """The ISTFT lives in torchlibrosa (absent): the restatement is pinned by definition (torch.istft computes the same
+    windowed overlap-add with squared-window normalisation) and by the STFT round trip."""
+    x = O.synth_clips(2, 30011, seed=13)
+    real, imag = O.stft_conv_dft(x)
+    y = O.istft(real, imag, x.shape[1])
+    assert y.shape == x.shape and y.dtype == torch.float32
+    assert float((y - x).abs().max()) < 1e-5
+    spec = torch.complex(real[:, 0].double(), imag[:, 0].double()).transpose(1, 2)
+    ref = torch.istft(spec, n_fft=O.N_FFT, hop_length=O.HOP, win_length=O.N_FFT, window=O.hann_periodic(), center=True,
+                      length=x.shape[1])
+    assert float((y.double() - ref).abs().max()) < 1e-6
+    # a shorter request keeps the head (torchlibrosa _trim_edges), linearity in the spectrum
+    assert torch.equal(O.istft(real, imag, 1000), y[:, :1000])
+    y2 = O.istft(2 * real, 2 * imag, x.shape[1])
+    assert float((y2 - 2 * y).abs().max()) < 1e-6
+
+
+def test_ssr_path_against_reference_golden(state, golden_fingerprint_ok):
+    """SURVEY.md 8(f) row 1 (next path): unet_v2 magnitude branch + input phase + ISTFT vs the reference module's output."""
+    g = load_golden("ssr_t64.npz")
+    ssr = _ssr_state(state)
+    wav = torch.from_numpy(g["wav"])[:, None, :]
+    with torch.no_grad():
+        sp, _, _ = O.wav_to_spectrogram_phase(wav)
+        mag = O.unet_v2_forward(ssr, sp)
+        out = O.ssr_forward(ssr, wav)
+    assert mag.shape == g["out_mag"].shape == (2, 1, 64, 1025)
+    assert float((mag - torch.from_numpy(g["out_mag"])).abs().max()) < 2e-5 * float(np.abs(g["out_mag"]).max())
+    assert bool((mag[..., 1024] == 0).all())                       # padded last bin (unet_v2.py:128)
+    assert out.shape == (2, 1, wav.shape[2])
+    assert float((out[:, 0] - torch.from_numpy(g["out"])).abs().max()) < 2e-5

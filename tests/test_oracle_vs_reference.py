@@ -61,3 +61,18 @@ def test_trim_center_matches_reference():
         est = torch.arange(float(le))[None, None]
         ref = torch.zeros(1, 1, lr)
         assert torch.equal(trim_center(est, ref)[0], O.trim_center(est, lr))
+
+
+def test_unet_v2_ssr_restatement_matches_reference(state):
+    """Next path: models/components/unet_v2.py imported unmodified vs the restatement."""
+    from voicefixer_main_b200.arch import UNET_PREFIX
+    ssr = {k.replace(UNET_PREFIX, "generator.unet."): v for k, v in state.items() if k.startswith(UNET_PREFIX)}
+    net = ref_import.build_reference_unet_v2(ssr)
+    for n in (63 * 441, 70 * 441 + 17):                   # T = 64 (no time padding) and T = 71 -> T' = 128
+        wav = O.synth_clips(1, n, seed=n)[:, None, :]
+        with torch.no_grad():
+            sp, _, _ = O.wav_to_spectrogram_phase(wav)
+            ref = net(sp, wav)["wav"]
+            mine = O.ssr_forward(ssr, wav)
+        assert ref.shape == mine.shape == (1, 1, n)
+        assert float((ref - mine).abs().max()) < 1e-5
