@@ -2,16 +2,20 @@
 //
 // Persistent, warp-specialised: each CTA loops over 128 x BN output tiles (tile = blockIdx.x + i * gridDim.x,
 // N tiles of one M tile adjacent so co-running CTAs share the A rows in L2).
-//   warp 0     : TMA producer - streams A (activation rows, shifted per tap) and B (packed weights) tiles into a
-//                `stages`-deep shared-memory ring that runs ahead across tile boundaries
-//                (SWIZZLE_128B rows for BK = 64, SWIZZLE_64B for BK = 32)
-//   warp 1     : TMEM owner + single-thread tcgen05.mma issuer; two main accumulators ping-pong in TMEM
+//   warp 0     : TMA producer - streams A (activation rows, shifted per tap; one 130..144-row "halo" box serves up to
+//                three row-adjacent taps) and B (packed weights) tiles into a `stages`-deep shared-memory ring that
+//                runs ahead across tile boundaries (SWIZZLE_128B rows for BK = 64, SWIZZLE_64B for BK = 32); in
+//                3-term mode the hi and lo planes of an operand arrive in one 4-D / 3-D box
+//   warp 1     : TMEM owner + single-thread tcgen05.mma issuer; 2 or 4 accumulator buffers rotate in TMEM
 //   warps 2..  : epilogue (4 or 8 warps; one TMEM lane = output row per thread, two warps share a lane quarter
 //                and split the column chunks)
+// Both issue loops are run by ONE elected thread each and read the flattened per-chunk table the CTA builds in
+// shared memory at start-up (ChunkDesc); their per-chunk instruction count bounds every small-tile layer, which
+// is what the table, the 32-bit descriptor arithmetic and the specialised issue bodies (issue_mmas) are for.
 //
 // Accumulation precision.  The tensor core adds into its fp32 accumulator with truncation, so one long chain
 // of K/16 MMAs drifts by ~0.5 ulp per instruction (measured 2e-4 on the UNet log-mel with one accumulator per
-// tile).  In 3-term mode the K loop is therefore cut into segments of 24 K steps that ping-pong between two TMEM
+// tile).  In 3-term mode the K loop is therefore cut into segments of 24 K steps that rotate through the TMEM
 // accumulator buffers; the epilogue warps add each finished segment into registers in fp32 round-to-nearest
 // ("promotion") while the tensor core already works on the next one.  Each buffer is [main | correction]: the
 // two small correction products (hi*lo, lo*hi) never mix into the main chain.  The same ping-pong is the tile double buffering
