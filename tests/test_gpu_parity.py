@@ -315,3 +315,25 @@ def test_longform_margins_vs_oracle(model, state):
     assert float((ours - ref).pow(2).mean().sqrt()) < WAV_RMS_TOL
     again = restore_longform(model, wav.cuda(), window_size=W, in_margin=M).cpu()
     assert torch.equal(again, ours)
+
+
+def test_handler_file_to_file(model, state, tmp_path, monkeypatch):
+    """handler() end to end (eval_gsr_voicefixer.py:37-77): PCM16 wav in -> restored PCM16 wav out, int16 conversion on
+    the GPU; checked against the oracle run on the decoded input."""
+    from voicefixer_main_b200 import handler as H
+    n = 44100 + 321
+    pcm_in = O.to_int16(O.synth_clips(1, n, seed=77)[0].clamp(-0.99, 0.99).numpy())
+    src, dst = str(tmp_path / "in.wav"), str(tmp_path / "out.wav")
+    H.save_pcm16(pcm_in, src)
+    monkeypatch.setattr(H, "model", model)
+    metrics = H.handler(src, dst, None, ckpt=None, device=model.device, needrefresh=False, meta={})
+    assert metrics == {}
+    got = H.load_wav(dst)
+    assert got.shape == (n,)
+    x = torch.from_numpy(pcm_in.astype(np.float32) / 32768.0)[None]
+    with torch.no_grad():
+        ref = O.restore(state, x, exact_stft=True)[0].numpy()
+    ref_pcm = O.to_int16(np.clip(ref, -1.0, 32767.0 / 32768.0)).astype(np.float64) / 32768.0
+    keep = np.abs(ref) < 0.999                                    # the +1.0 peak sample wraps in int16 (tested above)
+    d = got.astype(np.float64)[keep] - ref_pcm[keep]
+    assert float(np.sqrt(np.mean(d * d))) < WAV_RMS_TOL
