@@ -28,6 +28,8 @@ cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t s
 size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int tile_chunks);
 int gemm_tc_max_ctas(int bn);
 uint32_t gemm_tc_magic(uint32_t d, uint64_t nmax);
+cudaError_t launch_pair_tc(const PairParams& p, cudaStream_t stream);
+size_t pair_tc_smem_bytes(int C, int stages);
 cudaError_t launch_gemm_simt(const GemmSimtParams& p, cudaStream_t stream);
 }  // namespace vf
 
@@ -68,7 +70,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-enum OpKind { OP_GEMM, OP_FIRST, OP_POOL, OP_COND, OP_REFLECT, OP_TAIL, OP_FINALIZE, OP_MEMSET32 };
+enum OpKind { OP_GEMM, OP_FIRST, OP_POOL, OP_COND, OP_REFLECT, OP_TAIL, OP_FINALIZE, OP_MEMSET32, OP_PAIR };
 
 struct Op {
   OpKind kind;
@@ -77,6 +79,7 @@ struct Op {
   char label[48] = {0};
   GemmTcParams tc;
   GemmSimtParams simt;
+  PairParams pair;
   UnetFirstParams first;
   PoolParams pool;
   VocCondParams cond;
@@ -1011,10 +1014,62 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
       b.gemm(ops, ctx->voc_up[s], ASrc{prev, (int)Lprev, 0}, nullptr, taps, e, B, terms);
     }
     int curx = 0;
+    // EXPERIMENTAL, opt-in (VF_TUNE_FUSED_PAIR=1): one kernel per residual pair (pair_tc.cu), the intermediate stays in
+    // shared memory.  Its activated input and output planes must differ (a tile reads rows up to `dil` away from
+    // the ones another CTA is writing), so the pairs ping-pong between xa and a second plane.
+    const bool fused = getenv("VF_TUNE_FUSED_PAIR") && atoi(getenv("VF_TUNE_FUSED_PAIR")) == 1 && !ctx->validate_simt &&
+                       terms == 1 && (cout == 64 || cout == 128);
+    Planes xa2;
+    if (fused) xa2 = b.planes(B, (int)L, cout);
+    if (b.rc) return b.rc;
+    int cura = 0;
     for (int i = 0; i < c.voc_depth[s]; ++i) {
       int dil = 1;
       for (int q = 0; q < i % 10; ++q) dil *= 3;
       const bool last = i == c.voc_depth[s] - 1;
+      if (fused) {
+        Planes src = cura ? xa2 : xa;
+        Planes dst = (last && last_stage) ? tail_in : (cura ? xa : xa2);
+        Op op;
+        op.kind = OP_PAIR;
+        PairParams& pp = op.pair;
+        memset(&pp, 0, sizeof pp);
+        int mrc = b.make_map3(&pp.a_map, src.p.hi, cout, (int)L, src.img_rows, B, 64, true, GEMM_BM);
+        if (!mrc) mrc = b.make_map2(&pp.wa_map, ctx->voc_res_a[s][i].hi, ctx->voc_res_a[s][i].K, cout, 64, cout, true);
+        if (!mrc) mrc = b.make_map2(&pp.wb_map, ctx->voc_res_b[s][i].hi, ctx->voc_res_b[s][i].K, cout, 64, cout, true);
+        if (mrc) return mrc;
+        pp.bias_a = ctx->voc_res_a[s][i].bias;
+        pp.bias_b = ctx->voc_res_b[s][i].bias;
+        pp.resid_hi = xr[curx].p.hi; pp.resid_lo = xr[curx].p.lo;
+        if (!last) { pp.out_r_hi = xr[1 - curx].p.hi; pp.out_r_lo = xr[1 - curx].p.lo; }
+        pp.out_a = dst.p.hi;
+        pp.L = (int)L; pp.n_img = B; pp.C = cout; pp.dil = dil;
+        pp.out_img_rows = dst.img_rows;
+        pp.out_row0 = (last && last_stage) ? 3 : 0;
+        pp.tiles_per_img = (int)((L + 125) / 126);
+        const long total_tiles = (long)B * pp.tiles_per_img;
+        int ctas = cout == 64 ? 2 : 1, stages = 0;
+        for (; ctas >= 1; --ctas) {
+          const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
+          for (stages = 8; stages >= 2; --stages)
+            if (pair_tc_smem_bytes(cout, stages) <= per_cta) break;
+          if (stages >= 2) break;
+        }
+        if (ctas < 1 || stages < 2) return fail(ctx, VF_EINVAL, "fused pair: no configuration fits (C=%d)", cout);
+        pp.stages = stages;
+        pp.grid = (int)std::min<long>(total_tiles, (long)ctx->sm_count * ctas);
+        pp.magic_t = gemm_tc_magic((uint32_t)pp.tiles_per_img, (uint64_t)total_tiles);
+        pp.slope_h = c.voc_res_slope;
+        pp.slope_out = last ? c.voc_stage_slope : c.voc_res_slope;
+        pp.err = ctx->d_err;
+        op.flops = 2.0 * 2.0 * (double)B * L * cout * 3.0 * cout;
+        op.bytes = (double)B * L * cout * (2 + 4 + (last ? 0 : 4) + 2);
+        snprintf(op.label, sizeof op.label, "voc.res%d.%d.pair", s, i);
+        ops.push_back(op);
+        curx = 1 - curx;
+        cura = 1 - cura;
+        continue;
+      }
       {
         GemmEpilogue e = epi_plain((int)L, 0, cout, (int)L);
         e.bias = ctx->voc_res_a[s][i].bias;
@@ -1059,7 +1114,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
       p.wav = plan->d_voc_wav; p.peak_bits = plan->d_peak;
       ops.push_back(op);
     }
-    prev = xa;
+    prev = (fused && cura) ? xa2 : xa;
     Lprev = L;
     cin = cout;
   }
@@ -1118,7 +1173,7 @@ int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
     if (ctx->op_timing) {
       int rc = prof_mark(ctx, st);
       if (rc) return rc;
-      const char* kinds[] = {"gemm", "unet_first", "pool", "voc_condition", "reflect_fill", "voc_tail", "finalize", "memset"};
+      const char* kinds[] = {"gemm", "unet_first", "pool", "voc_condition", "reflect_fill", "voc_tail", "finalize", "memset", "pair"};
       ctx->prof.push_back({op.label[0] ? std::string(op.label) : std::string(kinds[op.kind]), op.flops, op.bytes, op.bn, op.bk, op.kind == OP_GEMM ? op.tc.prob.terms : 0});
     }
     switch (op.kind) {
@@ -1132,6 +1187,7 @@ int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
       case OP_TAIL: e = launch_voc_tail(op.tail, st); break;
       case OP_FINALIZE: e = launch_finalize(op.fin, st); break;
       case OP_MEMSET32: e = cudaMemsetAsync(op.ms.p, 0, op.ms.bytes, st); break;
+      case OP_PAIR: e = launch_pair_tc(op.pair, st); break;
     }
     if (e != cudaSuccess) return fail(ctx, VF_ECUDA, "kernel launch (op kind %d): %s", (int)op.kind, cudaGetErrorString(e));
     ctx->launches++;

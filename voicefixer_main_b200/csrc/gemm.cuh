@@ -112,6 +112,34 @@ struct GemmTcParams {
   GemmProblem prob;
 };
 
+// Fused residual pair of the vocoder stacks (pair_tc.cu, experimental / opt-in): x_new = x + conv_b(lrelu(conv_a(xa) + bias_a)) + bias_b
+struct PairParams {
+  CUtensorMap a_map;             // activated input plane lrelu(x), hi: [C, L, clips], box 64 x 128 x 1, SWIZZLE_128B
+  CUtensorMap wa_map, wb_map;    // packed K-major hi weights [K >= 3C, C], box 64 x C
+  const float* bias_a;
+  const float* bias_b;
+  const __half* resid_hi;        // x, hi/lo planes [clips, L, C]
+  const __half* resid_lo;
+  __half* out_r_hi;              // x_new raw planes (null for the last pair of a stage)
+  __half* out_r_lo;
+  __half* out_a;                 // lrelu(x_new, slope_out), hi plane [clips, out_img_rows, C], first row out_row0
+  int L, n_img, C, dil, out_img_rows, out_row0, tiles_per_img, stages, grid;
+  uint32_t magic_t;              // gemm_tc_magic(tiles_per_img, ...)
+  float slope_h, slope_out;
+  int* err;
+};
+
+__host__ __device__ inline uint32_t fast_div_pair(uint32_t n, uint32_t d, uint32_t magic) {
+#ifdef __CUDA_ARCH__
+  if (magic == 0u) return n;
+  if (magic == 0xffffffffu) return n / d;
+  return __umulhi(n, magic);
+#else
+  (void)magic;
+  return n / d;
+#endif
+}
+
 struct GemmSimtParams {            // validation kernel: same contract, plain pointers
   const __half* a_hi[2];
   const __half* a_lo[2];
