@@ -24,6 +24,9 @@ follows.  Pinning status:
   (requirements.txt:6; call site eval_gsr_voicefixer.py:66), source and weights
   absent -> PARITY UNPINNED.  `vocoder_forward` restates the published generator
   design under voicefixer_main_b200.arch.VocoderConfig.
+* next path (SSR): `unet_v2_forward` is PINNED (bit-identical to
+  models/components/unet_v2.py imported unmodified, golden ssr_t64.npz); `istft` restates
+  torchlibrosa's ISTFT (absent) and is pinned by torch.istft and the STFT round trip only.
 """
 import math
 from typing import Dict, Optional, Tuple
