@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from voicefixer_main_b200.longform import BoxcarOverlapAdd
+from voicefixer_main_b200.longform import BoxcarOverlapAdd, WindowedOverlapAdd
 
 REF = "/root/reference/tools/dsp/overlapadd_boxcar.py"
 CASES = [(1000, 256, 32), (1024, 256, 32), (200, 256, 32), (256, 256, 64), (513, 256, 255), (2049, 512, 100)]
@@ -101,3 +101,47 @@ def test_plan_and_argument_checks():
         BoxcarOverlapAdd(ToyNet(), 1, 256, 256)
     with pytest.raises(NotImplementedError):
         BoxcarOverlapAdd(ToyNet(), 2, 256, 32, reorder_chunks=True)
+
+
+# ------------------------------------------------------------------ windowed overlap-add (tools/dsp/overlapadd.py)
+REF_OLA = "/root/reference/tools/dsp/overlapadd.py"
+OLA_CASES = [(1000, 256, None), (1024, 256, 128), (300, 256, 64), (2049, 512, 256), (777, 128, 32)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_OLA), reason="reference tree not present")
+@pytest.mark.parametrize("n,w,hop", OLA_CASES)
+@pytest.mark.parametrize("windowed", [True, False])
+def test_windowed_ola_matches_reference(n, w, hop, windowed):
+    spec = importlib.util.spec_from_file_location("ref_overlapadd", REF_OLA)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    x = _signal(n)
+    ref_net, our_net = ToyNet(), ToyNet()
+    ref = mod.LambdaOverlapAdd(nnet=ref_net, n_src=1, window_size=w, hop_size=hop, window="hann", reorder_chunks=False)
+    ref.use_window = windowed
+    ours = WindowedOverlapAdd(our_net, n_src=1, window_size=w, hop_size=hop, window="hann" if windowed else None,
+                              reorder_chunks=False)
+    a, b = ref(x), ours(x)
+    assert a.shape == b.shape == (2, 1, n)
+    assert torch.equal(a, b)
+    assert ref_net.calls == our_net.calls
+
+
+@pytest.mark.parametrize("n,w,hop", OLA_CASES)
+def test_windowed_ola_batched_equals_sequential_and_cola(n, w, hop):
+    x = _signal(n, batch=2)
+    seq, bat = ToyNet(batch_invariant=False), ToyNet(batch_invariant=True)
+    a = WindowedOverlapAdd(seq, 1, w, hop, window="hanning", reorder_chunks=False)(x)
+    b = WindowedOverlapAdd(bat, 1, w, hop, window="hanning", reorder_chunks=False)(x)
+    assert torch.allclose(a, b, atol=1e-6)
+    assert len(bat.calls) == 1 and bat.calls[0][0] == 2 * len(seq.calls)   # the whole file in one call
+
+    class Identity:
+        batch_invariant = True
+
+        def __call__(self, t):
+            return {"wav": t[:, :1, :]}
+
+    if hop is None or 2 * hop == w:                 # periodic hann at 50 % overlap sums to one: identity in, identity out
+        y = WindowedOverlapAdd(Identity(), 1, w, hop, window="hann", reorder_chunks=False)(x)
+        assert torch.allclose(y, x, atol=1e-6)

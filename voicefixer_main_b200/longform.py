@@ -135,6 +135,74 @@ class BoxcarOverlapAdd:
     __call__ = forward
 
 
+class WindowedOverlapAdd:
+    """tools/dsp/overlapadd.py:338-484 (`LambdaOverlapAdd`, windowed): the signal is zero-padded by one window on both
+    sides, cut into windows of `window_size` every `hop_size` (default half a window), every window goes through
+    `nnet`, is multiplied by the synthesis window and overlap-added back (`:419-466`).  All windows have the same
+    length, so a batch-invariant network (the engine) processes the whole file in ONE call.
+
+    window: scipy window name ("hanning", the reference's default spelling, is accepted for "hann"), or None/False for
+    the unweighted average `frame / (window_size / hop_size)` (`:455-458`)."""
+
+    def __init__(self, nnet, n_src: Optional[int], window_size: int, hop_size: Optional[int] = None, window="hanning",
+                 reorder_chunks: bool = True, enable_grad: bool = False, device=None):
+        assert window_size % 2 == 0, "Window size must be even"          # :392
+        if reorder_chunks and n_src not in (None, 1):
+            raise NotImplementedError("source reordering (n_src > 1) is outside this path")
+        self.nnet = nnet
+        self.window_size = window_size
+        self.hop_size = hop_size if hop_size is not None else window_size // 2   # :396
+        self.n_src = n_src
+        self.in_channels = getattr(nnet, "in_channels", None)
+        self.enable_grad = enable_grad
+        if window:
+            from scipy.signal import get_window
+            name = "hann" if window == "hanning" else window          # scipy dropped the old alias
+            self.window = torch.from_numpy(get_window(name, window_size).astype("float32"))
+            self.use_window = True
+        else:
+            self.window = None
+            self.use_window = False
+
+    def ola_forward(self, x: torch.Tensor, key: str = "wav") -> torch.Tensor:
+        assert x.ndim == 3                                                  # :417
+        batch, channels, n_frames = x.shape
+        W, hop = self.window_size, self.hop_size
+        unfolded = F.unfold(x.unsqueeze(-1), kernel_size=(W, 1), padding=(W, 0), stride=(hop, 1))   # :421-426
+        n_chunks = unfolded.shape[-1]
+        unfolded = unfolded.view(batch, channels, W, n_chunks)              # :431
+        if getattr(self.nnet, "batch_invariant", False) and n_chunks > 1:
+            stack = unfolded.permute(3, 0, 1, 2).reshape(n_chunks * batch, channels, W).contiguous()
+            frames = self.nnet(stack)[key]
+            assert frames.ndim == 3, "nnet should return (batch, n_src, time)"
+            n_src = frames.shape[1]
+            frames = frames.reshape(n_chunks, batch * n_src, W)
+        else:
+            outs = []
+            n_src = None
+            for i in range(n_chunks):                                       # :434-459
+                f = self.nnet(unfolded[..., i])[key]
+                assert f.ndim == 3, "nnet should return (batch, n_src, time)"
+                n_src = f.shape[1]
+                outs.append(f.reshape(batch * n_src, -1))
+            frames = torch.stack(outs)
+        if self.n_src is not None:
+            assert n_src == self.n_src, "nnet should return (batch, n_src, time)"
+        if self.use_window:
+            frames = frames * self.window.to(frames)                        # :455-456
+        else:
+            frames = frames / (W / hop)                                     # :457-458
+        out = frames.reshape(n_chunks, batch * n_src, W).permute(1, 2, 0)   # :461-462
+        out = F.fold(out, (n_frames, 1), kernel_size=(W, 1), padding=(W, 0), stride=(hop, 1))   # :464-470
+        return out.squeeze(-1).reshape(batch, n_src, -1)
+
+    def forward(self, x: torch.Tensor, key: str = "wav") -> torch.Tensor:
+        with torch.autograd.set_grad_enabled(self.enable_grad):
+            return self.ola_forward(x, key=key)
+
+    __call__ = forward
+
+
 def restore_longform(model, wav: torch.Tensor, window_size: int = 44100 * 30, in_margin: int = 44100 * 2,
                      unify_energy: bool = False) -> torch.Tensor:
     """wav [B, N] on the model's device -> [B, N]: VoiceFixer.restore over 30 s windows with 2 s of context on
