@@ -16,6 +16,13 @@
  *                                 pre -> model -> from_log -> vocoder -> peak normalise -> trim_center
  *   vf_to_log / vf_from_log       tools/pytorch/pytorch_util.py:157-163
  *   vf_to_pcm16                   the int16 conversion of save_wave, tools/file/wav.py:22-24
+ *   vf_mel                        MelScale.forward on any spectrogram, tools/pytorch/mel_scale.py:52-64
+ *   vf_finalize                   peak normalise + trim_center, eval_gsr_voicefixer.py:68-72, tools/utils.py:57-70
+ *   vf_ssr_forward / vf_ssr_restore(_host) / vf_ssr_unet
+ *                                 SSR_UNet / GSR_UNet inference (BASELINE config 3): models/ssr_unet.py:140-155 ->
+ *                                 Generator.forward :51-54 -> unet_v2 UNetResComplex_100Mb.forward
+ *                                 models/components/unet_v2.py:86-148 (magnitude net, input phase, ISTFT)
+ *   vf_istft                      FDomainHelper.istft tools/pytorch/modules/fDomainHelper.py:30-32,127 (torchlibrosa ISTFT)
  *
  * Conventions: every function returns 0 on success or a negative VF_E* code and never throws; the message is
  * available from vf_last_error().  All tensor arguments are contiguous fp32.  Unless a name ends in `_host`,
@@ -73,6 +80,7 @@ typedef struct vf_config {
   int voc_tail_base;      /* 4 */
   double voc_mel_weight_a;
   double voc_mel_weight_b;
+  int voc_tail_tanh;      /* 1 (the generator ends in tanh); 0 leaves the tail linear - test configurations only */
 } vf_config;
 
 /* Fills *cfg with the reference defaults listed above. */
@@ -92,7 +100,10 @@ VF_API void vf_destroy(vf_ctx* ctx);
 VF_API const char* vf_last_error(vf_ctx* ctx);   /* ctx may be NULL: error of the last failed vf_create */
 
 /* Copies and packs the tensors (BN folded to per-channel affine, conv weights to K-major fp16 hi/lo
- * matrices, mel filterbank to its sparse form).  Synchronous.  Missing keys -> VF_ESTATE. */
+ * matrices, mel filterbank to its sparse form).  Synchronous.  "mel.fb" is required; of the three networks -
+ * "generator.analysis_module.*" (VoiceFixer's mel UNet; unet.py and unet_small.py share its keys), "vocoder.*",
+ * "generator.unet.*" (unet_v2 of SSR_UNet / GSR_UNet) - whichever are present are loaded, and a network that is
+ * present must be complete (missing key -> VF_ESTATE).  Entry points that need an absent network fail with VF_ESTATE. */
 VF_API int vf_load_weights(vf_ctx* ctx, const vf_tensor_desc* descs, int n);
 
 /* wav [B,N] -> mel_out [B,T,128] linear mel (T = 1 + N/hop); optional sp/cos/sin [B,T,1025] (NULL to skip). */
@@ -109,6 +120,11 @@ VF_API int64_t vf_vocoder_out_len(vf_ctx* ctx, int frames);
 
 /* Fused stages A -> B -> C + peak normalise + centre trim: wav [B,N] -> wav_out [B,N] (device pointers). */
 VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n_samples, float* wav_out, void* stream);
+/* vf_restore with per-call behaviour flags (re-entrant: nothing is stored in the context). */
+#define VF_RESTORE_UNIFY_ENERGY 1u   /* amp_to_original_f (tools/utils.py:50-55) as handler() applies it when
+                                        meta["unify_energy"] is set, eval_gsr_voicefixer.py:54-55 */
+VF_API int vf_restore_ex(vf_ctx* ctx, const float* wav, int batch, int64_t n_samples, float* wav_out, unsigned flags,
+                         void* stream);
 /* Same through HOST buffers (pinned for true asynchrony): H2D copy, vf_restore, D2H copy on `stream`.
  * The caller synchronises the stream before reading out_host. */
 VF_API int vf_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_t n_samples, float* out_host, void* stream);
@@ -116,6 +132,31 @@ VF_API int vf_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_
  * [B,T,128] (either may be NULL): the linear mel of stage A and the restored log10 mel of stage B. */
 VF_API int vf_restore_stages(vf_ctx* ctx, int batch, int64_t n_samples, float* mel_lin_out, float* log_mel_out,
                              void* stream);
+
+/* ---- SSR_UNet / GSR_UNet (unet_v2) path.  vf_ssr_forward = model(sp, wav)['wav'] of models/ssr_unet.py:145-155:
+ * sp [B,T,1025] is the network input (NULL: the STFT magnitude of wav itself, i.e. pre() fused in), wav [B,N] supplies
+ * the phase (unet_v2.py:96) and the output length; wav_out [B,N].  vf_ssr_restore(wav) == vf_ssr_forward(NULL, wav). */
+VF_API int vf_ssr_forward(vf_ctx* ctx, const float* sp, const float* wav, int batch, int64_t n_samples, float* wav_out,
+                          void* stream);
+VF_API int vf_ssr_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n_samples, float* wav_out, void* stream);
+VF_API int vf_ssr_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_t n_samples, float* out_host,
+                               void* stream);
+/* The magnitude branch alone (unet_v2.py:99-132): sp [B,T,1025] -> out_mag [B,T,1025] (last bin 0, F.pad :128). */
+VF_API int vf_ssr_unet(vf_ctx* ctx, const float* sp, int batch, int frames, float* mag_out, void* stream);
+/* Intermediates of the last vf_ssr_* call of this shape: input magnitude and predicted magnitude [B,T,1025]. */
+VF_API int vf_ssr_stages(vf_ctx* ctx, int batch, int64_t n_samples, float* sp_out, float* mag_out, void* stream);
+/* FDomainHelper.istft(real, imag, length): real, imag [B,T,1025] -> wav_out [B,length]. */
+VF_API int vf_istft(vf_ctx* ctx, const float* real, const float* imag, int batch, int frames, int64_t length,
+                    float* wav_out, void* stream);
+
+/* MelScale.forward on an arbitrary spectrogram view: mel_out[o, t, m] = sum_f specgram[o*stride_outer + f*stride_freq +
+ * t*stride_time] * fb[f, m]; strides in elements, mel_out [n_outer, frames, 128] contiguous (n_outer <= 65535). */
+VF_API int vf_mel(vf_ctx* ctx, const float* specgram, int64_t n_outer, int64_t frames, int64_t stride_outer,
+                  int64_t stride_freq, int64_t stride_time, float* mel_out, void* stream);
+/* eval_gsr_voicefixer.py:68-72 as one op: wav [B,len] -> per clip `if max|x| > 1: x /= max|x|`, then trim_center to n
+ * samples -> wav_out [B,n].  (handler() sees batch 1, so "per clip" is its semantics.) */
+VF_API int vf_finalize(vf_ctx* ctx, const float* wav, int batch, int64_t len, int64_t n_samples, float* wav_out,
+                       void* stream);
 
 VF_API int vf_to_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream);
 VF_API int vf_from_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream);
@@ -130,10 +171,13 @@ VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n_samples, size_t*
 /* Synchronises `stream`, reads and clears the sticky device flags.  VF_OK, VF_EDEVICE or VF_EASSERT. */
 VF_API int vf_check_errors(vf_ctx* ctx, void* stream);
 
-/* Options: "vocoder_terms" (1 or 3 fp16 split terms; "unet_terms" accepts only 3), "unify_energy" (1: vf_restore applies
- * amp_to_original_f, tools/utils.py:50-55, as handler() does when meta["unify_energy"] is set),
+/* Options: "vocoder_terms" (1 or 3 fp16 split terms; "unet_terms" accepts only 3), "unify_energy" (default flag of
+ * vf_restore / vf_restore_host; prefer vf_restore_ex's per-call flag), "plan_cache_mb" (cap on the device memory
+ * held by cached per-shape plans, least recently used evicted first; 0 = half of the free device memory),
  * "validate_simt" (1: run every GEMM on the SIMT validation kernel instead of tcgen05 - tests only). */
 VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value);
+/* Plans are cached per (path, batch, frames); the cache is bounded (see "plan_cache_mb"). */
+VF_API int vf_plan_cache_info(vf_ctx* ctx, int* n_plans, size_t* bytes, size_t* budget, int64_t* evicted);
 /* Number of kernels this context has launched since creation. */
 VF_API int64_t vf_launch_count(vf_ctx* ctx);
 

@@ -86,8 +86,26 @@ def main_ssr():
     print("ssr_t64 out rms", float(out.pow(2).mean().sqrt()))
 
 
+def main_small():
+    """the `unet_small` analysis module (models/components/unet_small.py) imported unmodified,
+    through Generator.forward's arithmetic (gsr_voicefixer.py:86-91: unet(to_log(mel)) + to_log(mel))."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_state(SEED)
+    net = ref_import.build_reference_unet_small(sd)
+    from tools.pytorch.pytorch_util import to_log
+    g = torch.Generator().manual_seed(77)
+    mel_orig = 10 ** (torch.randn(1, 1, 101, 128, generator=g) * 0.8 - 1.0)
+    with torch.no_grad():
+        out = net(to_log(mel_orig))["mel"] + to_log(mel_orig)
+    np.savez_compressed(os.path.join(GOLD, "stage_b_small_t101.npz"), mel_orig=mel_orig.numpy(), log_mel=out.numpy(),
+                        fingerprint=state_fingerprint(sd))
+    print("stage_b_small_t101 written")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ssr":
         main_ssr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "small":
+        main_small()
     else:
         main()

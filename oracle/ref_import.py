@@ -175,6 +175,27 @@ def build_reference_unet_v2(state: dict, prefix: str = "generator.unet."):
     return net
 
 
+def build_reference_unet_small(state: dict, prefix: str = "generator.analysis_module."):
+    """models/components/unet_small.py:12 (selected by `unet_small: true`, gsr_voicefixer.py:51-53) in eval mode with the
+    analysis-module tensors of `state`: its *Res1B blocks (modules.py:112-165) carry the same four ConvBlockRes and
+    key names as the *Res4B blocks of unet.py, so the mel UNet's state loads without renaming."""
+    install_shims()
+    cwd = os.getcwd()
+    os.chdir(REPO_ROOT)
+    try:
+        from models.components.unet_small import UNetResComplex_100Mb
+        net = UNetResComplex_100Mb(channels=1)
+    finally:
+        os.chdir(cwd)
+    own = net.state_dict()
+    sd = {k[len(prefix):]: v for k, v in state.items() if k.startswith(prefix) and k[len(prefix):] in own}
+    missing = [k for k in own if k not in sd]
+    assert not missing, missing[:5]
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    return net
+
+
 def reference_handler_batch(model, wav: torch.Tensor, seg_samples: int = 44100 * 60, collect=None):
     """The body of handler() (eval_gsr_voicefixer.py:41-75) driven on in-memory clips
     (librosa/soundfile I/O is out of scope), one clip at a time as the reference does."""

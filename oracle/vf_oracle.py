@@ -309,7 +309,7 @@ def vocoder_generator(sd, c: torch.Tensor, cfg: VocoderConfig, prefix: str = "vo
             x = x + h
         x = F.leaky_relu(x, cfg.stage_slope)
     x = F.conv1d(F.pad(x, (hk, hk), mode="reflect"), g("tail.weight"), g("tail.bias"))
-    return torch.tanh(x)
+    return torch.tanh(x) if getattr(cfg, "tail_tanh", True) else x
 
 
 def vocoder_forward(sd, mel: torch.Tensor, cfg: Optional[VocoderConfig] = None) -> torch.Tensor:

@@ -201,21 +201,6 @@ def test_handler_protocol_drop_in(model, state):
     assert float((fused.cpu() - out[0].cpu()).abs().max()) < 1e-5
 
 
-def test_unify_energy_matches_amp_to_original_f(model, state):
-    """handler() with meta["unify_energy"] (eval_gsr_voicefixer.py:54-55, tools/utils.py:50-55)."""
-    wav = O.synth_clips(2, 22050, seed=12)
-    with torch.no_grad():
-        ref = O.restore(state, wav, exact_stft=True, unify_energy=True)
-        plain = O.restore(state, wav, exact_stft=True)
-    out = model.restore(wav.cuda(), unify_energy=True).cpu()
-    model._engine().check_errors()
-    delta = float((ref - plain).pow(2).mean().sqrt())
-    assert delta > 1e-4                                             # the option really changes the output
-    assert float((out - ref).pow(2).mean().sqrt()) < 0.25 * delta   # and we follow it, not the plain path
-    back = model.restore(wav.cuda()).cpu()
-    assert float((back - plain).pow(2).mean().sqrt()) < 0.25 * delta
-
-
 def test_long_form_segment_loop(model, state, monkeypatch):
     """BASELINE config 5 path: handler()'s independent-segment loop (eval_gsr_voicefixer.py:47-75), checked
     against the oracle with a short segment length (ragged tail), then one real 60 s segment for size."""

@@ -76,3 +76,18 @@ def test_unet_v2_ssr_restatement_matches_reference(state):
             mine = O.ssr_forward(ssr, wav)
         assert ref.shape == mine.shape == (1, 1, n)
         assert float((ref - mine).abs().max()) < 1e-5
+
+
+def test_unet_small_is_the_same_network(ref_model, state):
+    """models/components/unet_small.py imported unmodified.  In this reference its *Res1B blocks
+    hold four ConvBlockRes each (modules.py:112-165), i.e. the layers and keys of unet.py: the product maps
+    `unet_small: true` onto the same plan, which this test justifies bit for bit."""
+    small = ref_import.build_reference_unet_small(state)
+    g = torch.Generator().manual_seed(4)
+    mel = 10 ** (torch.randn(1, 1, 101, 128, generator=g) - 1)
+    with torch.no_grad():
+        a = small(O.to_log(mel))["mel"] + O.to_log(mel)
+        b = ref_model(mel)["mel"]
+        c = O.generator_forward(state, mel)
+    assert torch.equal(a, b)
+    assert float((a - c).abs().max()) < 2e-5

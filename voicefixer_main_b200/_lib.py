@@ -6,7 +6,7 @@ with VF_ENODEVICE.  Nothing here computes on the data path; it only marshals poi
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p)
+from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200vf.so")
@@ -18,7 +18,10 @@ EXPORTS = [
     "vf_unet_mel", "vf_vocoder", "vf_vocoder_out_len", "vf_restore", "vf_restore_host", "vf_restore_stages",
     "vf_to_log", "vf_from_log", "vf_to_pcm16", "vf_workspace_bytes", "vf_check_errors", "vf_set_option", "vf_launch_count",
     "vf_enable_stage_timing", "vf_stage_times", "vf_selftest_gemm", "vf_enable_op_timing", "vf_op_count", "vf_op_info",
+    "vf_restore_ex", "vf_ssr_forward", "vf_ssr_restore", "vf_ssr_restore_host", "vf_ssr_unet", "vf_ssr_stages", "vf_istft",
+    "vf_mel", "vf_finalize", "vf_plan_cache_info",
 ]
+VF_RESTORE_UNIFY_ENERGY = 1
 
 
 class VfConfig(Structure):
@@ -27,7 +30,8 @@ class VfConfig(Structure):
                 ("voc_num_stages", c_int), ("voc_scales", c_int * 8), ("voc_depth", c_int * 8),
                 ("voc_stage_slope", c_float), ("voc_res_slope", c_float), ("voc_min_db", c_float),
                 ("voc_ref_db", c_float), ("voc_amp_floor", c_float), ("voc_tail_value", c_float),
-                ("voc_tail_base", c_int), ("voc_mel_weight_a", c_double), ("voc_mel_weight_b", c_double)]
+                ("voc_tail_base", c_int), ("voc_mel_weight_a", c_double), ("voc_mel_weight_b", c_double),
+                ("voc_tail_tanh", c_int)]
 
 
 class VfTensorDesc(Structure):
@@ -88,6 +92,16 @@ def load_library():
     lib.vf_op_count.argtypes = [P]
     lib.vf_op_info.argtypes = [P, c_int, POINTER(c_float), POINTER(c_double), POINTER(c_double), POINTER(c_int),
                                POINTER(c_int), POINTER(c_int), c_char_p, c_int]
+    lib.vf_restore_ex.argtypes = [P, P, c_int, c_int64, P, c_uint, P]
+    lib.vf_ssr_forward.argtypes = [P, P, P, c_int, c_int64, P, P]
+    lib.vf_ssr_restore.argtypes = [P, P, c_int, c_int64, P, P]
+    lib.vf_ssr_restore_host.argtypes = [P, P, c_int, c_int64, P, P]
+    lib.vf_ssr_unet.argtypes = [P, P, c_int, c_int, P, P]
+    lib.vf_ssr_stages.argtypes = [P, c_int, c_int64, P, P, P]
+    lib.vf_istft.argtypes = [P, P, P, c_int, c_int, c_int64, P, P]
+    lib.vf_mel.argtypes = [P, P, c_int64, c_int64, c_int64, c_int64, c_int64, P, P]
+    lib.vf_finalize.argtypes = [P, P, c_int, c_int64, c_int64, P, P]
+    lib.vf_plan_cache_info.argtypes = [P, POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int64)]
     _lib = lib
     return lib
 

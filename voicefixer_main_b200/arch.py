@@ -18,7 +18,8 @@ oracle/vf_oracle.py ("parity unpinned" by the reference itself).
 from dataclasses import dataclass, field
 from typing import List, Tuple
 
-UNET_PREFIX = "generator.analysis_module."
+UNET_PREFIX = "generator.analysis_module."      # VoiceFixer's mel UNet (models/gsr_voicefixer.py:50,139)
+SSR_PREFIX = "generator.unet."                  # unet_v2 inside SSR_UNet / GSR_UNet (models/ssr_unet.py:49, gsr_unet.py:49)
 
 ENC_CHANNELS = [(1, 32), (32, 64), (64, 128), (128, 256), (256, 384), (384, 384)]
 DEC_CHANNELS = [(384, 384), (384, 384), (384, 256), (256, 128), (128, 64), (64, 32)]
@@ -84,6 +85,7 @@ class VocoderConfig:
     mel_weight_a: float = 18.8927416350036
     mel_weight_b: float = 0.0269863588184314
     hop: int = 441
+    tail_tanh: bool = True        # False: linear tail (test configurations whose output exceeds |1|)
 
     def stage_channels(self) -> List[Tuple[int, int]]:
         c = self.channels

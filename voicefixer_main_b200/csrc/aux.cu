@@ -12,13 +12,15 @@ __device__ __forceinline__ float lrelu(float a, float slope) { return a > 0.f ? 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) unet_first_kernel(UnetFirstParams p) {
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)p.batch * p.Tp * 128;
+  const int Wp = p.W + 1;
+  const size_t total = (size_t)p.batch * p.Tp * Wp;
   if (pix >= total) return;
-  const int f = pix & 127;
-  const int t = (pix >> 7) % p.Tp;
-  const int b = (pix >> 7) / p.Tp;
+  const size_t row = pix / Wp;
+  const int f = (int)(pix - row * Wp);
+  const int t = (int)(row % p.Tp);
+  const int b = (int)(row / p.Tp);
   float out_a[32], out_r[32];
-  if (f == 127) {
+  if (f == p.W) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) { out_a[c] = 0.f; out_r[c] = 0.f; }
   } else {
@@ -30,8 +32,8 @@ __global__ void __launch_bounds__(128) unet_first_kernel(UnetFirstParams p) {
       for (int dw = 0; dw < 3; ++dw) {
         const int tt = t + dh - 1, ff = f + dw - 1;
         float v = 0.f;
-        if (tt >= 0 && tt < p.Tp && ff >= 0 && ff < 127) {
-          const float x = tt < p.T ? __ldg(p.logmel + ((size_t)b * p.T + tt) * 128 + ff) : 0.f;
+        if (tt >= 0 && tt < p.Tp && ff >= 0 && ff < p.W) {
+          const float x = tt < p.T ? __ldg(p.logmel + ((size_t)b * p.T + tt) * p.in_ld + ff) : 0.f;
           if (dh == 1 && dw == 1) xc = x;
           v = lrelu(fmaf(x, p.bn1_scale, p.bn1_shift), p.slope);
         }
@@ -45,6 +47,10 @@ __global__ void __launch_bounds__(128) unet_first_kernel(UnetFirstParams p) {
       out_a[c] = lrelu(fmaf(y, __ldg(p.bn2_scale + c), __ldg(p.bn2_shift + c)), p.slope);
       out_r[c] = fmaf(xc, __ldg(p.w_sc + c), __ldg(p.b_sc + c));
     }
+    bool ovf = false;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) ovf |= !(fabsf(out_a[c]) <= 65504.f);
+    if (ovf && p.err) atomicCAS(p.err, 0, ERR_FP16_OVERFLOW);
   }
   float4* rp = reinterpret_cast<float4*>(p.sc_raw + pix * 32);
 #pragma unroll
@@ -53,7 +59,7 @@ __global__ void __launch_bounds__(128) unet_first_kernel(UnetFirstParams p) {
   for (int i = 0; i < 4; ++i) split_store8(p.a2.hi, p.a2.lo, pix * 32 + 8 * i, out_a + 8 * i);
 }
 cudaError_t launch_unet_first(const UnetFirstParams& p, cudaStream_t stream) {
-  const size_t total = (size_t)p.batch * p.Tp * 128;
+  const size_t total = (size_t)p.batch * p.Tp * (p.W + 1);
   unet_first_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
@@ -61,7 +67,7 @@ cudaError_t launch_unet_first(const UnetFirstParams& p, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pool_kernel(PoolParams p) {
   const int cg = p.C / 8;
-  const int Ho = p.H / 2, Wpo = p.Wp / 2;
+  const int Ho = p.H / 2, Wpo = p.Wpo;
   const size_t total = (size_t)p.batch * Ho * Wpo * cg;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(256) pool_kernel(PoolParams p) {
   if (p.out_a.hi) split_store8(p.out_a.hi, p.out_a.lo, o, a);
 }
 cudaError_t launch_pool(const PoolParams& p, cudaStream_t stream) {
-  const size_t total = (size_t)p.batch * (p.H / 2) * (p.Wp / 2) * (p.C / 8);
+  const size_t total = (size_t)p.batch * (p.H / 2) * p.Wpo * (p.C / 8);
   pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) voc_tail_kernel(VocTailParams p)
   for (int o = 0; o < TAIL_RT; ++o) {
     const long t = t0 + r0 + o;
     if (t < p.L) {
-      const float y = tanhf(acc[o] + p.bias);
+      const float y = p.tanh_out ? tanhf(acc[o] + p.bias) : acc[o] + p.bias;
       p.wav[(size_t)b * p.L + t] = y;
       mag = fmaxf(mag, fabsf(y));
     }

@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -96,7 +97,25 @@ struct ConvBlockW {
   int cin = 0, cout = 0;
 };
 
+// One analysis ResUNet (models/components/unet.py / unet_small.py / unet_v2.py share the block structure and key names)
+struct UnetW {
+  bool loaded = false;
+  ConvBlockW enc[6][4], bott, dec[6][4], post;
+  GemmW dec_up[6];
+  Affine dec_bn1[6];
+  float first_bn1_scale = 1, first_bn1_shift = 0;
+  float* d_first_w1 = nullptr;
+  float* d_first_wsc = nullptr;
+  float* d_first_bsc = nullptr;
+  float* d_head_w = nullptr;
+  float head_b = 0;
+};
+
+enum PlanKind { PLAN_GSR = 0, PLAN_SSR = 1 };
+
 struct Plan {
+  int kind = PLAN_GSR;
+  uint64_t last_use = 0;
   int batch = 0, T = 0;
   long n_samples = 0;
   std::vector<void*> allocs;
@@ -111,6 +130,10 @@ struct Plan {
   float* d_band = nullptr;       // [B][2] low-band energy sums (unify_energy)
   unsigned int* d_peak = nullptr;
   long L = 0;
+  // SSR plans (unet_v2 + ISTFT)
+  float* d_sp = nullptr;         // [B, T, 1025] input magnitude
+  float* d_mag = nullptr;        // [B, T, 1025] predicted magnitude
+  float* d_frames = nullptr;     // [B, T, 2048] windowed inverse-DFT frames
   // op slots patched per call
   int fe_op = -1, cond_op = -1, fin_op = -1;
 };
@@ -137,16 +160,11 @@ struct vf_ctx {
   int *d_fb_f0 = nullptr, *d_fb_len = nullptr, *d_fb_ofs = nullptr;
   float* d_fb_val = nullptr;
   float* d_melw = nullptr;
-  // UNet weights
-  ConvBlockW enc[6][4], bott, dec[6][4], post;
-  GemmW dec_up[6];
-  Affine dec_bn1[6];
-  float first_bn1_scale = 1, first_bn1_shift = 0;
-  float* d_first_w1 = nullptr;
-  float* d_first_wsc = nullptr;
-  float* d_first_bsc = nullptr;
-  float* d_head_w = nullptr;
-  float head_b = 0;
+  // UNet weights: the mel-domain analysis module of VoiceFixer (prefix generator.analysis_module.) and the
+  // linear-spectrogram unet_v2 of SSR_UNet / GSR_UNet (prefix generator.unet.); either may be absent
+  UnetW gsr, ssr;
+  bool voc_loaded = false;
+  float* d_win_sq_inv = nullptr;   // ISTFT: 1 / clamp(overlap-added squared window, 1e-11), period hop (steady state)
   // vocoder weights
   std::vector<GemmW> voc_cond;
   GemmW voc_stem;
@@ -155,7 +173,11 @@ struct vf_ctx {
   float* d_tail_w = nullptr;
   float tail_b = 0;
   int voc_last_c = 64;
-  std::map<std::pair<int, long>, std::unique_ptr<Plan>> plans;
+  std::map<std::tuple<int, int, long>, std::unique_ptr<Plan>> plans;   // (kind, batch, frames)
+  uint64_t use_clock = 0;
+  size_t plan_bytes = 0;               // device bytes held by cached plans
+  size_t plan_budget = 0;              // cap for plan_bytes (LRU eviction); 0 = decide at first use from free memory
+  int64_t plans_evicted = 0;
   bool op_timing = false;
   struct ProfRec { std::string label; double flops, bytes; int bn, bk, terms; };
   std::vector<ProfRec> prof;
@@ -360,64 +382,55 @@ int build_tables(vf_ctx* ctx) {
   return upload(ctx, &ctx->d_melw, mw);
 }
 
-int load_all(vf_ctx* ctx) {
-  const std::string U = "generator.analysis_module.";
-  // mel filterbank -> sparse rows (each triangular filter is one contiguous run of bins)
-  {
-    NEED(fb, "mel.fb");
-    if (fb->shape.size() != 2 || fb->shape[0] != 1025 || fb->shape[1] != 128)
-      return fail(ctx, VF_EINVAL, "mel.fb must be [1025,128]");
-    std::vector<int> f0(128), len(128), ofs(128);
-    std::vector<float> val;
-    for (int m = 0; m < 128; ++m) {
-      int lo = -1, hi = -1;
-      for (int f = 0; f < 1025; ++f)
-        if (fb->v[(size_t)f * 128 + m] != 0.f) { if (lo < 0) lo = f; hi = f; }
-      if (lo < 0) { lo = 0; hi = -1; }
-      f0[m] = lo; len[m] = hi - lo + 1; ofs[m] = (int)val.size();
-      for (int f = lo; f <= hi; ++f) val.push_back(fb->v[(size_t)f * 128 + m]);
-    }
-    if (val.empty()) val.push_back(0.f);
-    int rc = upload(ctx, &ctx->d_fb_f0, f0); if (rc) return rc;
-    rc = upload(ctx, &ctx->d_fb_len, len); if (rc) return rc;
-    rc = upload(ctx, &ctx->d_fb_ofs, ofs); if (rc) return rc;
-    rc = upload(ctx, &ctx->d_fb_val, val); if (rc) return rc;
-  }
-  // UNet
+bool has_prefix(vf_ctx* ctx, const std::string& prefix) {
+  for (auto& kv : ctx->host_w)
+    if (kv.first.compare(0, prefix.size(), prefix) == 0) return true;
+  return false;
+}
+
+// One ResUNet under state-dict prefix U (unet.py:22-53 / unet_v2.py:46-77 registration names)
+int load_unet(vf_ctx* ctx, const std::string& U, UnetW* w) {
   for (int i = 0; i < 6; ++i)
     for (int j = 0; j < 4; ++j) {
       const std::string p = U + "encoder_block" + std::to_string(i + 1) + ".conv_block" + std::to_string(j + 1);
-      int rc = load_block(ctx, p, &ctx->enc[i][j], i == 0 && j == 0);
+      int rc = load_block(ctx, p, &w->enc[i][j], i == 0 && j == 0);
       if (rc) return rc;
     }
+  int rc;
   {
     const std::string p = U + "encoder_block1.conv_block1";
-    std::vector<float> s, h;
-    int rc = fold_bn(ctx, p + ".bn1", &s, &h); if (rc) return rc;
-    ctx->first_bn1_scale = s[0]; ctx->first_bn1_shift = h[0];
+    std::vector<float> sc, sh;
+    rc = fold_bn(ctx, p + ".bn1", &sc, &sh); if (rc) return rc;
+    w->first_bn1_scale = sc[0]; w->first_bn1_shift = sh[0];
     NEED(w1, p + ".conv1.weight"); NEED(scw, p + ".shortcut.weight"); NEED(scb, p + ".shortcut.bias");
-    rc = upload(ctx, &ctx->d_first_w1, w1->v); if (rc) return rc;
-    rc = upload(ctx, &ctx->d_first_wsc, scw->v); if (rc) return rc;
-    rc = upload(ctx, &ctx->d_first_bsc, scb->v); if (rc) return rc;
+    if (w1->shape.size() != 4 || w1->shape[1] != 1) return fail(ctx, VF_EINVAL, "%s.conv1.weight: channels_in must be 1", p.c_str());
+    rc = upload(ctx, &w->d_first_w1, w1->v); if (rc) return rc;
+    rc = upload(ctx, &w->d_first_wsc, scw->v); if (rc) return rc;
+    rc = upload(ctx, &w->d_first_bsc, scb->v); if (rc) return rc;
   }
-  int rc = load_block(ctx, U + "conv_block7", &ctx->bott, false); if (rc) return rc;
+  rc = load_block(ctx, U + "conv_block7", &w->bott, false); if (rc) return rc;
   for (int i = 0; i < 6; ++i) {
     const std::string p = U + "decoder_block" + std::to_string(i + 1);
     NEED(up, p + ".conv1.weight");
-    rc = pack_convT2d(ctx, &ctx->dec_up[i], *up); if (rc) return rc;
-    rc = upload_bn(ctx, p + ".bn1", &ctx->dec_bn1[i]); if (rc) return rc;
+    rc = pack_convT2d(ctx, &w->dec_up[i], *up); if (rc) return rc;
+    rc = upload_bn(ctx, p + ".bn1", &w->dec_bn1[i]); if (rc) return rc;
     for (int j = 0; j < 4; ++j) {
-      rc = load_block(ctx, p + ".conv_block" + std::to_string(j + 2), &ctx->dec[i][j], false);
+      rc = load_block(ctx, p + ".conv_block" + std::to_string(j + 2), &w->dec[i][j], false);
       if (rc) return rc;
     }
   }
-  rc = load_block(ctx, U + "after_conv_block1", &ctx->post, false); if (rc) return rc;
+  rc = load_block(ctx, U + "after_conv_block1", &w->post, false); if (rc) return rc;
   {
     NEED(hw, U + "after_conv2.weight"); NEED(hb, U + "after_conv2.bias");
-    rc = upload(ctx, &ctx->d_head_w, hw->v); if (rc) return rc;
-    ctx->head_b = hb->v[0];
+    rc = upload(ctx, &w->d_head_w, hw->v); if (rc) return rc;
+    w->head_b = hb->v[0];
   }
-  // vocoder
+  w->loaded = true;
+  return VF_OK;
+}
+
+int load_vocoder(vf_ctx* ctx) {
+  int rc;
   const vf_config& c = ctx->cfg;
   ctx->voc_cond.resize(c.voc_cond_layers);
   for (int i = 0; i < c.voc_cond_layers; ++i) {
@@ -454,6 +467,43 @@ int load_all(vf_ctx* ctx) {
     ctx->tail_b = b->v[0];
     ctx->voc_last_c = cl;
   }
+  ctx->voc_loaded = true;
+  return VF_OK;
+}
+
+const char* const GSR_PREFIX = "generator.analysis_module.";   // models/gsr_voicefixer.py:50,139
+const char* const SSR_PREFIX = "generator.unet.";              // models/ssr_unet.py:49, models/gsr_unet.py:49
+
+// Loads whichever of the three networks the descriptors hold (a VoiceFixer checkpoint: analysis module + vocoder;
+// an SSR_UNet / GSR_UNet checkpoint: generator.unet.*).  A network that is present must be complete.
+int load_all(vf_ctx* ctx) {
+  // mel filterbank -> sparse rows (each triangular filter is one contiguous run of bins)
+  {
+    NEED(fb, "mel.fb");
+    if (fb->shape.size() != 2 || fb->shape[0] != 1025 || fb->shape[1] != 128)
+      return fail(ctx, VF_EINVAL, "mel.fb must be [1025,128]");
+    std::vector<int> f0(128), len(128), ofs(128);
+    std::vector<float> val;
+    for (int m = 0; m < 128; ++m) {
+      int lo = -1, hi = -1;
+      for (int f = 0; f < 1025; ++f)
+        if (fb->v[(size_t)f * 128 + m] != 0.f) { if (lo < 0) lo = f; hi = f; }
+      if (lo < 0) { lo = 0; hi = -1; }
+      f0[m] = lo; len[m] = hi - lo + 1; ofs[m] = (int)val.size();
+      for (int f = lo; f <= hi; ++f) val.push_back(fb->v[(size_t)f * 128 + m]);
+    }
+    if (val.empty()) val.push_back(0.f);
+    int rc = upload(ctx, &ctx->d_fb_f0, f0); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_fb_len, len); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_fb_ofs, ofs); if (rc) return rc;
+    rc = upload(ctx, &ctx->d_fb_val, val); if (rc) return rc;
+  }
+  int rc = VF_OK, n_nets = 0;
+  if (has_prefix(ctx, GSR_PREFIX)) { rc = load_unet(ctx, GSR_PREFIX, &ctx->gsr); if (rc) return rc; ++n_nets; }
+  if (has_prefix(ctx, SSR_PREFIX)) { rc = load_unet(ctx, SSR_PREFIX, &ctx->ssr); if (rc) return rc; ++n_nets; }
+  if (has_prefix(ctx, "vocoder.")) { rc = load_vocoder(ctx); if (rc) return rc; ++n_nets; }
+  if (n_nets == 0)
+    return fail(ctx, VF_ESTATE, "no network in the state: expected keys under '%s', '%s' or 'vocoder.'", GSR_PREFIX, SSR_PREFIX);
   return VF_OK;
 }
 
@@ -768,13 +818,24 @@ std::vector<GemmTap> taps3x3(int Wp, int cin) {
 }
 
 struct Level {
-  int H, Wp, C, rows;
+  int H, W, Wp, C, rows;
   float* raw[2];
   Planes aX, aT, cat_r, cat_a, P_r, P_a;   // P_* : pooled output of this level (input of the next)
   float* P_raw = nullptr;
 };
 
-int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
+// Geometry of one UNet instance: the mel-domain analysis module (unet.py: W0 = 127 of 128 mel bins, decoders prune the
+// time axis only) or unet_v2 on linear magnitudes (unet_v2.py: W0 = 1024 of 1025 bins, both=True pruning).  Row pitch
+// of level l is Wp = (W0 >> l) + 1: one shared zero pad column per image row (see gemm.cuh).
+struct UnetGeom {
+  int W0;                 // valid frequency bins fed to the first block
+  const float* in;        // [B, T, W0 + 1] fp32 network input
+  const float* head_in;   // [B, T, W0 + 1] residual added to the head output (gsr_voicefixer.py:90) or null (unet_v2.py:132)
+  float* head_out;        // [B, T, W0 + 1]
+  const char* tag;        // label prefix for profiles
+};
+
+int build_unet(vf_ctx* ctx, Builder& b, Plan* plan, const UnetW& U, const UnetGeom& G) {
   const int B = plan->batch, T = plan->T;
   const int Tp = (T + 63) / 64 * 64;
   std::vector<Op>& ops = plan->unet;
@@ -783,7 +844,7 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
   Level lv[7];
   for (int l = 0; l < 7; ++l) {
     Level& L = lv[l];
-    L.H = Tp >> l; L.Wp = 128 >> l; L.C = l < 6 ? ENC_C[l] : 384; L.rows = L.H * L.Wp;
+    L.H = Tp >> l; L.W = G.W0 >> l; L.Wp = L.W + 1; L.C = l < 6 ? ENC_C[l] : 384; L.rows = L.H * L.Wp;
     L.raw[0] = b.alloc<float>((size_t)B * L.rows * L.C);
     L.raw[1] = b.alloc<float>((size_t)B * L.rows * L.C);
     L.aX = b.planes(B, L.rows, L.C);
@@ -791,15 +852,17 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
     if (l < 6) {
       L.cat_r = b.planes(B, L.rows, 2 * L.C);
       L.cat_a = b.planes(B, L.rows, 2 * L.C);
-      L.P_r = b.planes(B, L.rows / 4, L.C);
-      L.P_a = b.planes(B, L.rows / 4, L.C);
+      const size_t prow = (size_t)(L.H / 2) * ((L.W >> 1) + 1);      // rows of the pooled level
+      L.P_r = b.planes(B, (int)prow, L.C);
+      L.P_a = b.planes(B, (int)prow, L.C);
       // the consumer of the pooled tensor needs it in fp32 when its shortcut is the identity (Cin == Cout)
-      if (l == 5 || !ctx->enc[l + 1][0].has_sc) L.P_raw = b.alloc<float>((size_t)B * (L.rows / 4) * L.C);
+      if (l == 5 || !U.enc[l + 1][0].has_sc) L.P_raw = b.alloc<float>((size_t)B * prow * L.C);
     }
   }
   if (b.rc) return b.rc;
 
   std::string tag;   // profiling label of the block being emitted
+  const std::string pre = G.tag;
   // conv1 of a block: A -> aT with the block's bn2 + LeakyReLU
   auto conv1 = [&](const ConvBlockW& w, Level& L, const Planes& in) {
     b.label = tag + ".conv1";
@@ -827,18 +890,18 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
     Level& L = lv[l];
     int cur = 0;   // raw[cur] holds the block input
     for (int j = 0; j < 4; ++j) {
-      const ConvBlockW& w = ctx->enc[l][j];
-      tag = "enc" + std::to_string(l + 1) + ".b" + std::to_string(j + 1);
+      const ConvBlockW& w = U.enc[l][j];
+      tag = pre + "enc" + std::to_string(l + 1) + ".b" + std::to_string(j + 1);
       const float* resid = nullptr;
       const Planes* sc = nullptr;
       if (j == 0 && l == 0) {
         Op op; op.kind = OP_FIRST;
         UnetFirstParams& f = op.first;
         memset(&f, 0, sizeof f);
-        f.logmel = plan->d_logmel_in; f.batch = B; f.T = T; f.Tp = Tp;
-        f.bn1_scale = ctx->first_bn1_scale; f.bn1_shift = ctx->first_bn1_shift;
-        f.w1 = ctx->d_first_w1; f.bn2_scale = w.bn2.scale; f.bn2_shift = w.bn2.shift;
-        f.w_sc = ctx->d_first_wsc; f.b_sc = ctx->d_first_bsc; f.slope = S;
+        f.logmel = G.in; f.batch = B; f.T = T; f.Tp = Tp; f.W = G.W0; f.in_ld = G.W0 + 1;
+        f.bn1_scale = U.first_bn1_scale; f.bn1_shift = U.first_bn1_shift;
+        f.w1 = U.d_first_w1; f.bn2_scale = w.bn2.scale; f.bn2_shift = w.bn2.shift;
+        f.w_sc = U.d_first_wsc; f.b_sc = U.d_first_bsc; f.slope = S;
         f.a2 = L.aT.p; f.sc_raw = L.raw[0]; f.err = ctx->d_err;
         ops.push_back(op);
         resid = L.raw[0];      // precomputed shortcut(x) acts as the residual
@@ -857,11 +920,11 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
       e.out_raw = L.raw[dst];
       e.raw_ld = L.C;
       if (j < 3) {
-        const ConvBlockW& nx = ctx->enc[l][j + 1];
+        const ConvBlockW& nx = U.enc[l][j + 1];
         set_out_a(e, L.aX, 0, nx.bn1.scale, nx.bn1.shift, ACT_LRELU, S);
       } else {
         // skip connection: raw and activated halves of the decoder's concat buffer (modules.py:215)
-        const ConvBlockW& dblk = ctx->dec[5 - l][0];
+        const ConvBlockW& dblk = U.dec[5 - l][0];
         e.out_r = OutPlane{L.cat_r.p.hi, L.cat_r.p.lo, 2 * L.C, L.C};
         set_out_a(e, L.cat_a, L.C, dblk.bn1.scale + L.C, dblk.bn1.shift + L.C, ACT_LRELU, S);
       }
@@ -872,8 +935,8 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
     Op op; op.kind = OP_POOL;
     PoolParams& p = op.pool;
     memset(&p, 0, sizeof p);
-    const ConvBlockW& nx = l < 5 ? ctx->enc[l + 1][0] : ctx->bott;
-    p.in = L.raw[cur]; p.batch = B; p.H = L.H; p.Wp = L.Wp; p.C = L.C;
+    const ConvBlockW& nx = l < 5 ? U.enc[l + 1][0] : U.bott;
+    p.in = L.raw[cur]; p.batch = B; p.H = L.H; p.Wp = L.Wp; p.C = L.C; p.Wpo = (L.W >> 1) + 1;
     p.out_r = L.P_r.p; p.out_a = L.P_a.p; p.out_raw = L.P_raw;
     p.a_scale = nx.bn1.scale; p.a_shift = nx.bn1.shift; p.slope = S; p.err = ctx->d_err;
     ops.push_back(op);
@@ -881,11 +944,11 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
   // ---------------- bottleneck (conv_block7, identity shortcut) -> decoder_block1.bn1 + ReLU
   {
     Level& L = lv[6];
-    tag = "bottleneck";
-    conv1(ctx->bott, L, lv[5].P_a);
+    tag = pre + "bottleneck";
+    conv1(U.bott, L, lv[5].P_a);
     GemmEpilogue e = epi_plain(L.rows, L.Wp, 384, L.rows);
-    set_out_a(e, L.aX, 0, ctx->dec_bn1[0].scale, ctx->dec_bn1[0].shift, ACT_LRELU, 0.f);
-    conv2(ctx->bott, L, nullptr, lv[5].P_raw, e);
+    set_out_a(e, L.aX, 0, U.dec_bn1[0].scale, U.dec_bn1[0].shift, ACT_LRELU, 0.f);
+    conv2(U.bott, L, nullptr, lv[5].P_raw, e);
   }
   // ---------------- decoder
   for (int k = 0; k < 6; ++k) {
@@ -897,19 +960,20 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
       memset(&e, 0, sizeof e);
       e.map = MAP_CONVT2D; e.rows_in = Lin.rows; e.Wp = Lin.Wp; e.cout = cout; e.out_img_rows = L.rows;
       e.out_rows_valid = L.rows;
-      const ConvBlockW& blk = ctx->dec[k][0];
+      e.ct_out_wp = L.Wp;      // 2 * Lin.Wp (time-only prune, modules.py:209) or 2 * Lin.Wp - 1 (both=True, modules.py:207-208)
+      const ConvBlockW& blk = U.dec[k][0];
       e.out_r = OutPlane{L.cat_r.p.hi, L.cat_r.p.lo, 2 * L.C, 0};
       set_out_a(e, L.cat_a, 0, blk.bn1.scale, blk.bn1.shift, ACT_LRELU, S);
       std::vector<GemmTap> taps;
       for (int dh = 0; dh < 2; ++dh)
         for (int dw = 0; dw < 2; ++dw) taps.push_back(GemmTap{-(dh * Lin.Wp + dw), 0, 0, 0, cin});
-      b.label = "dec" + std::to_string(k + 1) + ".convT";
-      b.gemm(ops, ctx->dec_up[k], ASrc{Lin.aX, Lin.rows, 0}, nullptr, taps, e, B, terms);
+      b.label = pre + "dec" + std::to_string(k + 1) + ".convT";
+      b.gemm(ops, U.dec_up[k], ASrc{Lin.aX, Lin.rows, 0}, nullptr, taps, e, B, terms);
     }
     int cur = 0;
     for (int j = 0; j < 4; ++j) {
-      const ConvBlockW& w = ctx->dec[k][j];
-      tag = "dec" + std::to_string(k + 1) + ".b" + std::to_string(j + 2);
+      const ConvBlockW& w = U.dec[k][j];
+      tag = pre + "dec" + std::to_string(k + 1) + ".b" + std::to_string(j + 2);
       const float* resid = nullptr;
       const Planes* sc = nullptr;
       if (j == 0) { conv1(w, L, L.cat_a); sc = &L.cat_r; }
@@ -917,25 +981,25 @@ int build_unet(vf_ctx* ctx, Builder& b, Plan* plan) {
       GemmEpilogue e = epi_plain(L.rows, L.Wp, w.cout, L.rows);
       const int dst = j == 0 ? 0 : 1 - cur;
       if (j < 3) {
-        const ConvBlockW& nx = ctx->dec[k][j + 1];
+        const ConvBlockW& nx = U.dec[k][j + 1];
         e.out_raw = L.raw[dst]; e.raw_ld = L.C;
         set_out_a(e, L.aX, 0, nx.bn1.scale, nx.bn1.shift, ACT_LRELU, S);
       } else if (k < 5) {
-        set_out_a(e, L.aX, 0, ctx->dec_bn1[k + 1].scale, ctx->dec_bn1[k + 1].shift, ACT_LRELU, 0.f);   // ReLU, modules.py:213
+        set_out_a(e, L.aX, 0, U.dec_bn1[k + 1].scale, U.dec_bn1[k + 1].shift, ACT_LRELU, 0.f);   // ReLU, modules.py:213
       } else {
         e.out_raw = L.raw[dst]; e.raw_ld = L.C;
-        set_out_a(e, L.aX, 0, ctx->post.bn1.scale, ctx->post.bn1.shift, ACT_LRELU, S);
+        set_out_a(e, L.aX, 0, U.post.bn1.scale, U.post.bn1.shift, ACT_LRELU, S);
       }
       conv2(w, L, sc, resid, e);
       cur = dst;
     }
     if (k == 5) {   // after_conv_block1 + after_conv2 head + log-mel residual
-      tag = "post";
-      conv1(ctx->post, L, L.aX);
+      tag = pre + "post";
+      conv1(U.post, L, L.aX);
       GemmEpilogue e = epi_plain(L.rows, L.Wp, 32, L.rows);
-      e.head_w = ctx->d_head_w; e.head_b = ctx->head_b;
-      e.head_in = plan->d_logmel_in; e.head_out = plan->d_logmel_out; e.head_T = T;
-      conv2(ctx->post, L, nullptr, L.raw[cur], e);
+      e.head_w = U.d_head_w; e.head_b = U.head_b;
+      e.head_in = G.head_in; e.head_out = G.head_out; e.head_T = T;
+      conv2(U.post, L, nullptr, L.raw[cur], e);
     }
   }
   return b.rc;
@@ -1111,7 +1175,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
       VocTailParams& p = op.tail;
       memset(&p, 0, sizeof p);
       p.in = tail_in.p; p.batch = B; p.L = (int)L; p.C = cout; p.terms = terms; p.w = ctx->d_tail_w; p.bias = ctx->tail_b;
-      p.wav = plan->d_voc_wav; p.peak_bits = plan->d_peak;
+      p.wav = plan->d_voc_wav; p.peak_bits = plan->d_peak; p.tanh_out = c.voc_tail_tanh;
       ops.push_back(op);
     }
     prev = (fused && cura) ? xa2 : xa;
@@ -1121,38 +1185,124 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
   return b.rc;
 }
 
-int get_plan(vf_ctx* ctx, int batch, int frames, Plan** out) {
-  const auto key = std::make_pair(batch, (long)frames);
+// SSR / GSR-UNet plan (models/ssr_unet.py:145-155 -> unet_v2.py:86-148): STFT magnitude -> unet_v2 on 1024 bins -> the
+// predicted magnitude with the input's phase -> ISTFT.  Frames and the magnitude planes are the only extra buffers.
+int build_ssr(vf_ctx* ctx, Builder& b, Plan* plan) {
+  const size_t sp_n = (size_t)plan->batch * plan->T * 1025;
+  plan->d_sp = b.alloc<float>(sp_n);
+  plan->d_mag = b.alloc<float>(sp_n);
+  plan->d_frames = b.alloc<float>((size_t)plan->batch * plan->T * 2048);
+  if (b.rc) return b.rc;
+  UnetGeom g{1024, plan->d_sp, nullptr, plan->d_mag, "ssr."};
+  return build_unet(ctx, b, plan, ctx->ssr, g);
+}
+
+void free_plan(Plan* plan) {
+  for (void* p : plan->allocs) cudaFree(p);
+  plan->allocs.clear();
+}
+
+void drop_all_plans(vf_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->plans) free_plan(kv.second.get());
+  ctx->plans.clear();
+  ctx->plan_bytes = 0;
+}
+
+// Plans are cached per (kind, batch, frames) - a file-dependent tail segment or a ragged last chunk gets its own
+// shape - so the cache is bounded: least-recently-used plans are freed once the cached workspaces exceed the budget
+// (option "plan_cache_mb"; default: half of the device memory that was free at the first plan).  The reference
+// handler runs in constant memory (eval_gsr_voicefixer.py:49-74); so does a run over any number of distinct lengths.
+int evict_plans(vf_ctx* ctx, size_t incoming, const Plan* keep) {
+  if (ctx->plan_budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return fail(ctx, VF_ECUDA, "cudaMemGetInfo failed");
+    ctx->plan_budget = std::max<size_t>((free_b + ctx->plan_bytes) / 2, (size_t)1 << 30);
+  }
+  bool synced = false;
+  while (!ctx->plans.empty() && ctx->plan_bytes + incoming > ctx->plan_budget) {
+    auto victim = ctx->plans.end();
+    for (auto it = ctx->plans.begin(); it != ctx->plans.end(); ++it)
+      if (it->second.get() != keep && (victim == ctx->plans.end() || it->second->last_use < victim->second->last_use)) victim = it;
+    if (victim == ctx->plans.end()) break;
+    if (!synced) { cudaDeviceSynchronize(); synced = true; }     // the victim may still be executing on some stream
+    ctx->plan_bytes -= std::min(ctx->plan_bytes, victim->second->bytes);
+    free_plan(victim->second.get());
+    ctx->plans.erase(victim);
+    ctx->plans_evicted++;
+  }
+  return VF_OK;
+}
+
+int build_ssr(vf_ctx* ctx, Builder& b, Plan* plan);
+
+int get_plan(vf_ctx* ctx, int kind, int batch, int frames, Plan** out) {
+  const auto key = std::make_tuple(kind, batch, (long)frames);
   auto it = ctx->plans.find(key);
-  if (it != ctx->plans.end()) { *out = it->second.get(); return VF_OK; }
+  if (it != ctx->plans.end()) { it->second->last_use = ++ctx->use_clock; *out = it->second.get(); return VF_OK; }
   if (!ctx->loaded) return fail(ctx, VF_ESTATE, "weights not loaded");
+  if (kind == PLAN_GSR && !(ctx->gsr.loaded && ctx->voc_loaded))
+    return fail(ctx, VF_ESTATE, "this entry point needs the analysis module (generator.analysis_module.*) and the vocoder (vocoder.*) weights");
+  if (kind == PLAN_SSR && !ctx->ssr.loaded)
+    return fail(ctx, VF_ESTATE, "this entry point needs the unet_v2 weights (generator.unet.*)");
+  // make room first: a failed cudaMalloc half way through a plan is slower to recover from than an early eviction
+  {
+    size_t est = 0;
+    for (auto& kv : ctx->plans)
+      if (std::get<0>(kv.first) == kind) {     // bytes scale with batch * padded frames
+        const double r = ((double)batch * ((frames + 63) / 64 * 64)) / ((double)kv.second->batch * ((kv.second->T + 63) / 64 * 64));
+        est = (size_t)(r * (double)kv.second->bytes);
+        break;
+      }
+    int rc = evict_plans(ctx, est, nullptr);
+    if (rc) return rc;
+  }
   std::unique_ptr<Plan> plan(new Plan);
-  plan->batch = batch; plan->T = frames;
+  plan->kind = kind; plan->batch = batch; plan->T = frames;
   Builder b{ctx, plan.get()};
-  const size_t mel_n = (size_t)batch * frames * 128;
-  plan->d_mel = b.alloc<float>(mel_n);
-  plan->d_logmel_in = b.alloc<float>(mel_n);
-  plan->d_logmel_out = b.alloc<float>(mel_n);
-  plan->d_band = b.alloc<float>(2 * (size_t)batch);
-  int rc = b.rc;
-  if (!rc) rc = build_unet(ctx, b, plan.get());
-  if (!rc) rc = build_vocoder(ctx, b, plan.get());
+  int rc = VF_OK;
+  if (kind == PLAN_GSR) {
+    const size_t mel_n = (size_t)batch * frames * 128;
+    plan->d_mel = b.alloc<float>(mel_n);
+    plan->d_logmel_in = b.alloc<float>(mel_n);
+    plan->d_logmel_out = b.alloc<float>(mel_n);
+    plan->d_band = b.alloc<float>(2 * (size_t)batch);
+    rc = b.rc;
+    UnetGeom g{127, plan->d_logmel_in, plan->d_logmel_in, plan->d_logmel_out, ""};
+    if (!rc) rc = build_unet(ctx, b, plan.get(), ctx->gsr, g);
+    if (!rc) rc = build_vocoder(ctx, b, plan.get());
+  } else {
+    rc = build_ssr(ctx, b, plan.get());
+  }
+  if (rc == VF_ECUDA && !ctx->plans.empty()) {
+    // out of memory with other plans cached: drop them all and retry once
+    free_plan(plan.get());
+    cudaGetLastError();
+    drop_all_plans(ctx);
+    return get_plan(ctx, kind, batch, frames, out);
+  }
   if (rc) {
-    for (void* p : plan->allocs) cudaFree(p);
+    free_plan(plan.get());
     return rc;
   }
+  plan->last_use = ++ctx->use_clock;
+  ctx->plan_bytes += plan->bytes;
   *out = plan.get();
+  Plan* raw = plan.get();
   ctx->plans[key] = std::move(plan);
-  return VF_OK;
+  return evict_plans(ctx, 0, raw);
 }
 
 // staging buffers for the host-pointer entry point, grown on demand
 int ensure_io(vf_ctx* ctx, Plan* plan, long n) {
   if (plan->n_samples >= n && plan->d_wav) return VF_OK;
+  const size_t before = plan->bytes;
   Builder b{ctx, plan};
   plan->d_wav = b.alloc<float>((size_t)plan->batch * n);
   plan->d_out = b.alloc<float>((size_t)plan->batch * n);
   plan->n_samples = n;
+  ctx->plan_bytes += plan->bytes - before;
   return b.rc;
 }
 
@@ -1235,6 +1385,7 @@ VF_API void vf_default_config(vf_config* c) {
   c->voc_stage_slope = 0.2f; c->voc_res_slope = 0.01f; c->voc_min_db = -115.f; c->voc_ref_db = 20.f;
   c->voc_amp_floor = 1e-5f; c->voc_tail_value = -4.f; c->voc_tail_base = 4;
   c->voc_mel_weight_a = 18.8927416350036; c->voc_mel_weight_b = 0.0269863588184314;
+  c->voc_tail_tanh = 1;
 }
 
 VF_API const char* vf_last_error(vf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -1280,9 +1431,9 @@ VF_API void vf_destroy(vf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  for (auto& kv : ctx->plans)
-    for (void* p : kv.second->allocs) cudaFree(p);
+  for (auto& kv : ctx->plans) free_plan(kv.second.get());
   for (void* p : ctx->allocs) cudaFree(p);
+  for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   delete ctx;
@@ -1325,7 +1476,7 @@ VF_API int vf_unet_mel(vf_ctx* ctx, const float* mel_lin, int batch, int frames,
   if (!mel_lin || !logmel_out || batch <= 0 || frames <= 0) return fail(ctx, VF_EINVAL, "vf_unet_mel: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   Plan* plan;
-  rc = get_plan(ctx, batch, frames, &plan);
+  rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
   const size_t n = (size_t)batch * frames * 128;
   CK(launch_to_log(mel_lin, plan->d_logmel_in, n, ctx->d_err + 1, st));
@@ -1347,7 +1498,7 @@ VF_API int vf_vocoder(vf_ctx* ctx, const float* mel_lin, int batch, int frames, 
   if (!mel_lin || !wav_out || batch <= 0 || frames <= 0) return fail(ctx, VF_EINVAL, "vf_vocoder: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   Plan* plan;
-  rc = get_plan(ctx, batch, frames, &plan);
+  rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
   Op& cop = plan->vocoder[plan->cond_op];
   cop.cond.mel = mel_lin;
@@ -1361,14 +1512,10 @@ VF_API int vf_vocoder(vf_ctx* ctx, const float* mel_lin, int batch, int frames, 
   return VF_OK;
 }
 
-VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
-  int rc = check_ready(ctx);
-  if (rc) return rc;
-  if (!wav || !wav_out || batch <= 0) return fail(ctx, VF_EINVAL, "vf_restore: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
+static int restore_impl(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, unsigned flags, cudaStream_t st) {
   const int frames = frames_of(ctx, (long)n);
   Plan* plan;
-  rc = get_plan(ctx, batch, frames, &plan);
+  int rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
   if (ctx->op_timing) ctx->prof.clear();
   const bool tm = ctx->timing;
@@ -1386,7 +1533,7 @@ VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float
   {   // eval_gsr_voicefixer.py:54-55: amp_to_original_f when meta["unify_energy"]
     Op& cop = plan->vocoder[plan->cond_op];
     cop.cond.band_sums = nullptr;
-    if (ctx->unify_energy) {
+    if (flags & VF_RESTORE_UNIFY_ENERGY) {
       CK(cudaMemsetAsync(plan->d_band, 0, 2 * (size_t)batch * sizeof(float), st));
       CK(launch_band_energy(plan->d_mel, plan->d_logmel_out, batch, frames, plan->d_band, st));
       ctx->launches++;
@@ -1409,21 +1556,193 @@ VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float
   return VF_OK;
 }
 
+VF_API int vf_restore_ex(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, unsigned flags, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!wav || !wav_out || batch <= 0) return fail(ctx, VF_EINVAL, "vf_restore: bad arguments");
+  if (flags & ~(unsigned)VF_RESTORE_UNIFY_ENERGY) return fail(ctx, VF_EINVAL, "vf_restore_ex: unknown flag bits 0x%x", flags);
+  return restore_impl(ctx, wav, batch, n, wav_out, flags, (cudaStream_t)stream);
+}
+
+VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
+  return vf_restore_ex(ctx, wav, batch, n, wav_out, ctx && ctx->unify_energy ? VF_RESTORE_UNIFY_ENERGY : 0u, stream);
+}
+
 VF_API int vf_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_t n, float* out_host, void* stream) {
   int rc = check_ready(ctx);
   if (rc) return rc;
   if (!wav_host || !out_host || batch <= 0) return fail(ctx, VF_EINVAL, "vf_restore_host: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   Plan* plan;
-  rc = get_plan(ctx, batch, frames_of(ctx, (long)n), &plan);
+  rc = get_plan(ctx, PLAN_GSR, batch, frames_of(ctx, (long)n), &plan);
   if (rc) return rc;
   rc = ensure_io(ctx, plan, (long)n);
   if (rc) return rc;
   const size_t bytes = (size_t)batch * n * 4;
   CK(cudaMemcpyAsync(plan->d_wav, wav_host, bytes, cudaMemcpyHostToDevice, st));
-  rc = vf_restore(ctx, plan->d_wav, batch, n, plan->d_out, stream);
+  rc = restore_impl(ctx, plan->d_wav, batch, n, plan->d_out, ctx->unify_energy ? VF_RESTORE_UNIFY_ENERGY : 0u, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(out_host, plan->d_out, bytes, cudaMemcpyDeviceToHost, st));
+  return VF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- SSR / GSR-UNet path
+static int ssr_impl(vf_ctx* ctx, Plan* plan, const float* sp, const float* wav, int batch, int64_t n, float* wav_out, cudaStream_t st) {
+  const int frames = plan->T;
+  if (ctx->op_timing) ctx->prof.clear();
+  const bool tm = ctx->timing;
+  if (tm) {
+    for (auto& e : ctx->ev)
+      if (!e) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(ctx->ev[0], st));
+  }
+  int rc = VF_OK;
+  if (!sp) {     // SSR_UNet.pre (ssr_unet.py:140-143): the magnitude of the input itself
+    rc = run_frontend(ctx, wav, batch, (long)n, nullptr, nullptr, plan->d_sp, nullptr, nullptr, st);
+    if (rc) return rc;
+  }
+  if (tm) CK(cudaEventRecord(ctx->ev[1], st));
+  plan->unet[0].first.logmel = sp ? sp : plan->d_sp;       // unet_v2.forward(sp, wav): the caller's sp feeds the net
+  rc = run_ops(ctx, plan->unet, st);
+  if (rc) return rc;
+  if (tm) CK(cudaEventRecord(ctx->ev[2], st));
+  IstftFramesParams fp;
+  memset(&fp, 0, sizeof fp);
+  fp.mag = plan->d_mag; fp.wav = wav; fp.n = (long)n; fp.batch = batch; fp.T = frames;
+  fp.window = ctx->d_window; fp.tw1024 = ctx->d_tw1024; fp.tw2048 = ctx->d_tw2048; fp.frames = plan->d_frames;
+  CK(launch_istft_frames(fp, st));
+  IstftOlaParams op;
+  memset(&op, 0, sizeof op);
+  op.frames = plan->d_frames; op.batch = batch; op.T = frames; op.length = (long)n; op.window = ctx->d_window;
+  op.out = wav_out; op.out_ld = (long)n;
+  CK(launch_istft_ola(op, st));
+  ctx->launches += 2;
+  if (tm) { CK(cudaEventRecord(ctx->ev[3], st)); CK(cudaEventRecord(ctx->ev[4], st)); ctx->ev_valid = true; }
+  return VF_OK;
+}
+
+VF_API int vf_ssr_forward(vf_ctx* ctx, const float* sp, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!wav || !wav_out || batch <= 0) return fail(ctx, VF_EINVAL, "vf_ssr_forward: bad arguments");
+  if (n <= 1024) return fail(ctx, VF_EINVAL, "reflect padding needs more than n_fft/2 = 1024 samples (got %ld)", (long)n);
+  Plan* plan;
+  rc = get_plan(ctx, PLAN_SSR, batch, frames_of(ctx, (long)n), &plan);
+  if (rc) return rc;
+  return ssr_impl(ctx, plan, sp, wav, batch, n, wav_out, (cudaStream_t)stream);
+}
+
+VF_API int vf_ssr_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
+  return vf_ssr_forward(ctx, nullptr, wav, batch, n, wav_out, stream);
+}
+
+VF_API int vf_ssr_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_t n, float* out_host, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!wav_host || !out_host || batch <= 0) return fail(ctx, VF_EINVAL, "vf_ssr_restore_host: bad arguments");
+  if (n <= 1024) return fail(ctx, VF_EINVAL, "reflect padding needs more than n_fft/2 = 1024 samples (got %ld)", (long)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* plan;
+  rc = get_plan(ctx, PLAN_SSR, batch, frames_of(ctx, (long)n), &plan);
+  if (rc) return rc;
+  rc = ensure_io(ctx, plan, (long)n);
+  if (rc) return rc;
+  const size_t bytes = (size_t)batch * n * 4;
+  CK(cudaMemcpyAsync(plan->d_wav, wav_host, bytes, cudaMemcpyHostToDevice, st));
+  rc = ssr_impl(ctx, plan, nullptr, plan->d_wav, batch, n, plan->d_out, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_host, plan->d_out, bytes, cudaMemcpyDeviceToHost, st));
+  return VF_OK;
+}
+
+VF_API int vf_ssr_unet(vf_ctx* ctx, const float* sp, int batch, int frames, float* mag_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!sp || !mag_out || batch <= 0 || frames <= 0) return fail(ctx, VF_EINVAL, "vf_ssr_unet: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* plan;
+  rc = get_plan(ctx, PLAN_SSR, batch, frames, &plan);
+  if (rc) return rc;
+  if (ctx->op_timing) ctx->prof.clear();
+  plan->unet[0].first.logmel = sp;
+  rc = run_ops(ctx, plan->unet, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(mag_out, plan->d_mag, (size_t)batch * frames * 1025 * 4, cudaMemcpyDeviceToDevice, st));
+  return VF_OK;
+}
+
+VF_API int vf_ssr_stages(vf_ctx* ctx, int batch, int64_t n, float* sp_out, float* mag_out, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  Plan* plan;
+  const int frames = frames_of(ctx, (long)n);
+  rc = get_plan(ctx, PLAN_SSR, batch, frames, &plan);
+  if (rc) return rc;
+  const size_t bytes = (size_t)batch * frames * 1025 * 4;
+  if (sp_out) CK(cudaMemcpyAsync(sp_out, plan->d_sp, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (mag_out) CK(cudaMemcpyAsync(mag_out, plan->d_mag, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return VF_OK;
+}
+
+VF_API int vf_istft(vf_ctx* ctx, const float* real, const float* imag, int batch, int frames, int64_t length, float* wav_out, void* stream) {
+  if (!ctx || !real || !imag || !wav_out || batch <= 0 || frames <= 0 || length <= 0) return ctx ? fail(ctx, VF_EINVAL, "vf_istft: bad arguments") : VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (length + 1024 > (int64_t)(frames - 1) * ctx->cfg.hop + 2048)
+    return fail(ctx, VF_EINVAL, "vf_istft: %d frames cover %ld samples, fewer than length %ld + n_fft/2", frames, (long)(frames - 1) * ctx->cfg.hop + 2048, (long)length);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* frames_buf = nullptr;           // stream-ordered scratch: no plan is tied to a bare ISTFT
+  CK(cudaMallocAsync((void**)&frames_buf, (size_t)batch * frames * 2048 * 4, st));
+  IstftFramesParams fp;
+  memset(&fp, 0, sizeof fp);
+  fp.real = real; fp.imag = imag; fp.batch = batch; fp.T = frames;
+  fp.window = ctx->d_window; fp.tw1024 = ctx->d_tw1024; fp.tw2048 = ctx->d_tw2048; fp.frames = frames_buf;
+  cudaError_t e1 = launch_istft_frames(fp, st);
+  IstftOlaParams op;
+  memset(&op, 0, sizeof op);
+  op.frames = frames_buf; op.batch = batch; op.T = frames; op.length = (long)length; op.window = ctx->d_window;
+  op.out = wav_out; op.out_ld = (long)length;
+  cudaError_t e2 = e1 == cudaSuccess ? launch_istft_ola(op, st) : e1;
+  cudaFreeAsync(frames_buf, st);
+  if (e2 != cudaSuccess) return fail(ctx, VF_ECUDA, "istft launch: %s", cudaGetErrorString(e2));
+  ctx->launches += 2;
+  return VF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- stand-alone boundary ops
+VF_API int vf_mel(vf_ctx* ctx, const float* specgram, int64_t n_outer, int64_t frames, int64_t stride_outer, int64_t stride_freq,
+                  int64_t stride_time, float* mel_out, void* stream) {
+  if (!ctx || !specgram || !mel_out || n_outer <= 0 || frames <= 0 || n_outer > 65535) return ctx ? fail(ctx, VF_EINVAL, "vf_mel: bad arguments") : VF_EINVAL;
+  if (!ctx->d_fb_val) return fail(ctx, VF_ESTATE, "mel filterbank not loaded (call vf_load_weights first)");
+  CK(cudaSetDevice(ctx->device));
+  MelParams p;
+  memset(&p, 0, sizeof p);
+  p.in = specgram; p.n_outer = (long)n_outer; p.T = (long)frames; p.so = (long)stride_outer; p.sf = (long)stride_freq; p.st = (long)stride_time;
+  p.out = mel_out; p.fb_f0 = ctx->d_fb_f0; p.fb_len = ctx->d_fb_len; p.fb_ofs = ctx->d_fb_ofs; p.fb_val = ctx->d_fb_val;
+  CK(launch_mel(p, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+
+VF_API int vf_finalize(vf_ctx* ctx, const float* wav, int batch, int64_t len, int64_t n, float* wav_out, void* stream) {
+  if (!ctx || !wav || !wav_out || batch <= 0 || len <= 0 || n <= 0) return ctx ? fail(ctx, VF_EINVAL, "vf_finalize: bad arguments") : VF_EINVAL;
+  const long d = (long)len - (long)n;
+  // trim_center (tools/utils.py:57-70) for an estimate at least as long as the reference; d == 1 is the reference's
+  // empty-slice case (est[..., 0:-0])
+  if (d < 0 || d == 1) return fail(ctx, VF_EINVAL, "vf_finalize: estimate length %ld vs reference %ld is not a trim_center case the path produces", (long)len, (long)n);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* peak = nullptr;
+  CK(cudaMallocAsync((void**)&peak, (size_t)batch * 4, st));
+  CK(cudaMemsetAsync(peak, 0, (size_t)batch * 4, st));
+  cudaError_t e1 = launch_peak(wav, batch, (long)len, peak, st);
+  FinalizeParams f;
+  memset(&f, 0, sizeof f);
+  f.wav = wav; f.peak_bits = peak; f.batch = batch; f.L = (long)len; f.n = (long)n; f.skip = d / 2;
+  f.out = wav_out; f.out_ld = (long)n; f.out_off = 0;
+  cudaError_t e2 = e1 == cudaSuccess ? launch_finalize(f, st) : e1;
+  cudaFreeAsync(peak, st);
+  if (e2 != cudaSuccess) return fail(ctx, VF_ECUDA, "finalize launch: %s", cudaGetErrorString(e2));
+  ctx->launches += 2;
   return VF_OK;
 }
 
@@ -1432,7 +1751,7 @@ VF_API int vf_restore_stages(vf_ctx* ctx, int batch, int64_t n, float* mel_lin_o
   if (rc) return rc;
   Plan* plan;
   const int frames = frames_of(ctx, (long)n);
-  rc = get_plan(ctx, batch, frames, &plan);
+  rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
   const size_t bytes = (size_t)batch * frames * 128 * 4;
   if (mel_lin_out) CK(cudaMemcpyAsync(mel_lin_out, plan->d_mel, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -1467,7 +1786,7 @@ VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n, size_t* bytes) 
   int rc = check_ready(ctx);
   if (rc) return rc;
   Plan* plan;
-  rc = get_plan(ctx, batch, frames_of(ctx, (long)n), &plan);
+  rc = get_plan(ctx, PLAN_GSR, batch, frames_of(ctx, (long)n), &plan);
   if (rc) return rc;
   if (bytes) *bytes = plan->bytes + ctx->weight_bytes;
   return VF_OK;
@@ -1502,21 +1821,31 @@ VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value) {
   } else if (k == "validate_simt") {
     slot = &ctx->validate_simt;
     value = value ? 1 : 0;
+  } else if (k == "plan_cache_mb") {
+    if (value < 0) return fail(ctx, VF_EINVAL, "plan_cache_mb must be >= 0 (0: half of the free device memory)");
+    ctx->plan_budget = (size_t)value << 20;
+    if (value) return evict_plans(ctx, 0, nullptr);
+    return VF_OK;
   } else {
     return fail(ctx, VF_EINVAL, "unknown option '%s'", key);
   }
   if (*slot != value) {   // plans bake the option in: drop them
-    cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
-    for (auto& kv : ctx->plans)
-      for (void* p : kv.second->allocs) cudaFree(p);
-    ctx->plans.clear();
+    drop_all_plans(ctx);
     *slot = value;
   }
   return VF_OK;
 }
 
 VF_API int64_t vf_launch_count(vf_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+VF_API int vf_plan_cache_info(vf_ctx* ctx, int* n_plans, size_t* bytes, size_t* budget, int64_t* evicted) {
+  if (!ctx) return VF_EINVAL;
+  if (n_plans) *n_plans = (int)ctx->plans.size();
+  if (bytes) *bytes = ctx->plan_bytes;
+  if (budget) *budget = ctx->plan_budget;
+  if (evicted) *evicted = ctx->plans_evicted;
+  return VF_OK;
+}
 
 VF_API int vf_enable_stage_timing(vf_ctx* ctx, int enable) {
   if (!ctx) return VF_EINVAL;

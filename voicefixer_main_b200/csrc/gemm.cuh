@@ -64,6 +64,8 @@ struct GemmEpilogue {
   int out_row0;        // row offset of output row 0 (slack for reflection padding)
   int out_rows_valid;  // MAP_CONVT1D: rows [0, out_rows_valid) exist
   int ct_stride, ct_pad;
+  int ct_out_wp;       // MAP_CONVT2D: row pitch of the output level (2*Wp for the mel UNet, modules.py:209 prunes time only;
+                       // 2*Wp - 1 for unet_v2's both=True pruning, modules.py:207-208: the column past the pitch is dropped)
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [n_img * rows_in, resid_ld] or null (MAP_PLAIN only)
   int resid_ld;
@@ -79,8 +81,8 @@ struct GemmEpilogue {
   float slope;
   const float* head_w;   // fused 1x1 head over the 32 channels of the row, or null
   float head_b;
-  const float* head_in;  // log-mel input  [n_img, head_T, 128]
-  float* head_out;       // log-mel output [n_img, head_T, 128]
+  const float* head_in;  // residual input [n_img, head_T, Wp] added to the head (log-mel, gsr_voicefixer.py:90), or null
+  float* head_out;       // [n_img, head_T, Wp]: bins 0..Wp-2 = head + bias (+ head_in), bin Wp-1 = 0 (+ head_in): F.pad, unet.py:99
   int head_T;
   int* err;
 };
@@ -179,8 +181,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int img, i
   } else if (e.map == MAP_CONVT2D) {
     const int h = r / e.Wp, w = r - h * e.Wp;
     const int ph = phase >> 1, pw = phase & 1;
-    orow = (size_t)img * e.out_img_rows + (size_t)(2 * h + ph) * (2 * e.Wp) + 2 * w + pw;
-    pad = (w == e.Wp - 1) && (pw == 1);
+    const int col = 2 * w + pw;
+    if (col >= e.ct_out_wp) return;          // both=True prune: column past the output pitch
+    orow = (size_t)img * e.out_img_rows + (size_t)(2 * h + ph) * e.ct_out_wp + col;
+    pad = col == e.ct_out_wp - 1;
   } else {
     const long t = (long)r * e.ct_stride + phase - e.ct_pad;
     if (t < 0 || t >= e.out_rows_valid) return;
@@ -240,14 +244,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int img, i
   }
 }
 
-// unet.py:96-100 + gsr_voicefixer.py:90: out = head(x) padded with a zero bin, plus the input log-mel.
+// unet.py:96-100 + gsr_voicefixer.py:90: out = head(x) padded with a zero bin, plus the input log-mel;
+// unet_v2.py:125-132: the same head without the residual (the output is the magnitude itself).
 __device__ __forceinline__ void epilogue_head(const GemmEpilogue& e, int img, int r, float head_acc) {
   if (!e.head_w || r >= e.rows_in) return;
-  const int t = r >> 7, f = r & 127;
+  const int t = r / e.Wp, f = r - t * e.Wp;
   if (t >= e.head_T) return;
-  const size_t idx = ((size_t)img * e.head_T + t) * 128 + f;
-  const float x = __ldg(e.head_in + idx);
-  e.head_out[idx] = (f < 127) ? (head_acc + e.head_b) + x : x;
+  const size_t idx = ((size_t)img * e.head_T + t) * e.Wp + f;
+  const float y = (f < e.Wp - 1) ? head_acc + e.head_b : 0.f;
+  e.head_out[idx] = e.head_in ? y + __ldg(e.head_in + idx) : y;
 }
 
 }  // namespace vf

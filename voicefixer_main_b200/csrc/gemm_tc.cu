@@ -433,8 +433,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           if (row_ok) {
             if (map == MAP_CONVT2D) {
               const int ph = phase >> 1, pw = phase & 1;
-              orow = (uint32_t)((size_t)img * e.out_img_rows + (size_t)(2 * cth + ph) * (2 * Wp) + 2 * ctw + pw);
-              flags = kRowValid | ((ctw == Wp - 1 && pw == 1) ? kRowPad : 0);
+              const int col = 2 * ctw + pw;
+              if (col < e.ct_out_wp) {         // both=True pruning drops the column past the output pitch
+                orow = (uint32_t)((size_t)img * e.out_img_rows + (size_t)(2 * cth + ph) * e.ct_out_wp + col);
+                flags = kRowValid | (col == e.ct_out_wp - 1 ? kRowPad : 0);
+              }
             } else {
               const long t = (long)r * e.ct_stride + phase - e.ct_pad;
               if (t >= 0 && t < e.out_rows_valid) {

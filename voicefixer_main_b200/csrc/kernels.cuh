@@ -33,8 +33,10 @@ struct PlanePtr {
 // encoder_block1.conv_block1: BN(1ch) -> LeakyReLU -> Conv3x3 1->32, then bn2 -> LeakyReLU of the same
 // block fused in (the only consumer), plus the 1->32 1x1 shortcut of the raw input (modules.py:263-271).
 struct UnetFirstParams {
-  const float* logmel;   // [batch, T, 128]; bins 0..126 feed the UNet (unet.py:78)
+  const float* logmel;   // [batch, T, in_ld]; bins 0..W-1 feed the UNet (unet.py:78: log-mel, W = 127 of 128;
+                         // unet_v2.py:108: linear magnitude, W = 1024 of 1025)
   int batch, T, Tp;      // Tp = T padded to a multiple of 64 with zero *input* rows (unet.py:75-77)
+  int W, in_ld;          // valid bins per frame / input row stride; the planes use row pitch Wp = W + 1
   float bn1_scale, bn1_shift;
   const float* w1;       // [32][9]
   const float* bn2_scale;  // [32]
@@ -42,8 +44,8 @@ struct UnetFirstParams {
   const float* w_sc;     // [32] shortcut weight
   const float* b_sc;     // [32] shortcut bias
   float slope;
-  PlanePtr a2;           // [batch, Tp*128, 32] act(bn2(conv1(...))), pad column zero
-  float* sc_raw;         // [batch, Tp*128, 32] fp32 shortcut(x), pad column zero
+  PlanePtr a2;           // [batch, Tp*Wp, 32] act(bn2(conv1(...))), pad column zero
+  float* sc_raw;         // [batch, Tp*Wp, 32] fp32 shortcut(x), pad column zero
   int* err;
 };
 cudaError_t launch_unet_first(const UnetFirstParams& p, cudaStream_t stream);
@@ -52,7 +54,8 @@ cudaError_t launch_unet_first(const UnetFirstParams& p, cudaStream_t stream);
 struct PoolParams {
   const float* in;       // [batch, H*Wp, C] fp32
   int batch, H, Wp, C;
-  PlanePtr out_r;        // [batch, (H/2)*(Wp/2), C] pooled raw
+  int Wpo;               // output row pitch = (Wp - 1) / 2 + 1 (floor pooling of the W = Wp - 1 valid columns + pad column)
+  PlanePtr out_r;        // [batch, (H/2)*Wpo, C] pooled raw
   PlanePtr out_a;        // act(scale*pooled+shift)
   float* out_raw;        // fp32 pooled or null
   const float* a_scale;
@@ -91,6 +94,7 @@ cudaError_t launch_reflect_fill(PlanePtr planes, int batch, int L, int C, int pa
 struct VocTailParams {
   PlanePtr in;           // [batch, L + 6, C]
   int batch, L, C, terms;
+  int tanh_out;          // 1: tanh on the output (the generator's last op); 0: linear (test configurations that exceed |1|)
   const float* w;        // [7][C]
   float bias;
   float* wav;            // [batch, L]
@@ -109,5 +113,50 @@ struct FinalizeParams {
 };
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream);
 cudaError_t launch_pcm16(const float* in, int16_t* out, size_t n, cudaStream_t stream);
+
+// max |wav| per clip as float bits (atomicMax), for the stand-alone peak normalise + trim entry point.
+cudaError_t launch_peak(const float* wav, int batch, long L, unsigned int* peak_bits, cudaStream_t stream);
+
+// MelScale.forward (tools/pytorch/mel_scale.py:52-64) as a stand-alone op on any [..., freq, time] view:
+// out[o, t, m] = sum_f in[o * so + f * sf + t * st] * fb[f, m] with the filterbank in its sparse form.
+struct MelParams {
+  const float* in;
+  long n_outer, T;
+  long so, sf, st;       // input strides (elements) of the outer, frequency and time axes
+  float* out;            // [n_outer, T, 128] contiguous
+  const int* fb_f0;
+  const int* fb_len;
+  const int* fb_ofs;
+  const float* fb_val;
+};
+cudaError_t launch_mel(const MelParams& p, cudaStream_t stream);
+
+// ISTFT (FDomainHelper.istft, fDomainHelper.py:30-32,127 -> torchlibrosa ISTFT: n_fft = win = 2048, hop 441, periodic
+// hann, center): stage 1 writes the windowed inverse-DFT frames, stage 2 overlap-adds them in a fixed order and divides
+// by the overlap-added squared window (clamped at 1e-11).  Stage 1 takes the spectrum either as (real, imag), or -
+// unet_v2.py:96,136-139 fused - as a magnitude plus the waveform whose STFT phase it is to carry:
+// real = mag * cos, imag = mag * sin with cos, sin = re/|X|, im/|X| of the input (fDomainHelper.py:62-64).
+struct IstftFramesParams {
+  const float* real;     // [batch, T, 1025] or null
+  const float* imag;
+  const float* mag;      // [batch, T, 1025] (with wav) or null
+  const float* wav;      // [batch, n]
+  long n;
+  int batch, T;
+  const float* window;   // [2048]
+  const float2* tw1024;
+  const float2* tw2048;
+  float* frames;         // [batch, T, 2048]
+};
+cudaError_t launch_istft_frames(const IstftFramesParams& p, cudaStream_t stream);
+struct IstftOlaParams {
+  const float* frames;   // [batch, T, 2048]
+  int batch, T;
+  long length;           // output samples per clip: y[n_fft/2 : n_fft/2 + length]
+  const float* window;
+  float* out;            // [batch, out_ld]
+  long out_ld;
+};
+cudaError_t launch_istft_ola(const IstftOlaParams& p, cudaStream_t stream);
 
 }  // namespace vf

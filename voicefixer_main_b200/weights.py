@@ -12,7 +12,7 @@ from typing import Dict
 
 import torch
 
-from .arch import UNET_PREFIX, VocoderConfig, unet_keys, vocoder_keys
+from .arch import SSR_PREFIX, UNET_PREFIX, VocoderConfig, unet_keys, vocoder_keys
 
 
 def _xavier(shape, gen, transposed=False):
@@ -73,3 +73,9 @@ def make_state(seed: int = 1234, cfg: VocoderConfig = None) -> Dict[str, torch.T
     sd = make_unet_state(seed)
     sd.update(make_vocoder_state(cfg, seed + 1))
     return sd
+
+
+def make_ssr_state(seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """unet_v2 (models/components/unet_v2.py) has the mel UNet's parameter shapes: the same seeded tensors under the
+    SSR_UNet / GSR_UNet prefix (models/ssr_unet.py:49)."""
+    return {k.replace(UNET_PREFIX, SSR_PREFIX): v for k, v in make_unet_state(seed).items()}
