@@ -188,12 +188,13 @@ VF_API int vf_stage_times(vf_ctx* ctx, float ms[4]);
 
 /* Per-launch profile: with op timing enabled, the next vf_restore records a CUDA event before every kernel of
  * the UNet and vocoder launch chains.  vf_op_info(i) synchronises and returns the device time of launch i
- * together with its ALGORITHMIC flops / minimum HBM bytes (the reference op's own counts), the tcgen05 tile
+ * together with its ALGORITHMIC flops / minimum HBM bytes (the reference op's own counts), the flops the tensor
+ * cores actually executed for it (3 MMAs per product in 3-term mode, tile / phase padding, identity taps), the tcgen05 tile
  * (bn, bk, fp16 split terms; 0 for non-GEMM kernels) and a label such as "enc3.b2.conv1".  For roofline reporting only. */
 VF_API int vf_enable_op_timing(vf_ctx* ctx, int enable);
 VF_API int vf_op_count(vf_ctx* ctx);
 VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, int* terms,
-                      char* label, int label_cap);
+                      char* label, int label_cap, double* exec_flops /* nullable: tensor-core flops actually issued */);
 
 /* Self-test of one flat-shift GEMM configuration: random fp16 hi/lo planes through the tcgen05 kernel and
  * the SIMT validation kernel; returns max |difference| and max |value|.  Synchronous. */

@@ -71,7 +71,7 @@ def test_batched_schedule_equals_sequential(n, w, m):
     x = _signal(n, batch=3)
     seq, bat = ToyNet(batch_invariant=False), ToyNet(batch_invariant=True)
     a = BoxcarOverlapAdd(seq, 1, w, m)(x)
-    b = BoxcarOverlapAdd(bat, 1, w, m)(x)
+    b = BoxcarOverlapAdd(bat, 1, w, m, max_batch=None)(x)
     assert torch.allclose(a, b, atol=1e-6)
     n_chunks = -(-n // w)
     assert len(seq.calls) == n_chunks
@@ -132,7 +132,7 @@ def test_windowed_ola_batched_equals_sequential_and_cola(n, w, hop):
     x = _signal(n, batch=2)
     seq, bat = ToyNet(batch_invariant=False), ToyNet(batch_invariant=True)
     a = WindowedOverlapAdd(seq, 1, w, hop, window="hanning", reorder_chunks=False)(x)
-    b = WindowedOverlapAdd(bat, 1, w, hop, window="hanning", reorder_chunks=False)(x)
+    b = WindowedOverlapAdd(bat, 1, w, hop, window="hanning", reorder_chunks=False, max_batch=None)(x)
     assert torch.allclose(a, b, atol=1e-6)
     assert len(bat.calls) == 1 and bat.calls[0][0] == 2 * len(seq.calls)   # the whole file in one call
 
@@ -145,3 +145,30 @@ def test_windowed_ola_batched_equals_sequential_and_cola(n, w, hop):
     if hop is None or 2 * hop == w:                 # periodic hann at 50 % overlap sums to one: identity in, identity out
         y = WindowedOverlapAdd(Identity(), 1, w, hop, window="hann", reorder_chunks=False)(x)
         assert torch.allclose(y, x, atol=1e-6)
+
+
+def test_max_batch_bounds_the_rows_per_call():
+    """the stacked schedules run `max_batch` rows per nnet call (workspace grows with batch x length), with
+    results identical to the unbounded stack; an n_src > 1 network with reorder_chunks is refused, not silently skipped."""
+    x = _signal(20 * 256 + 17, batch=2)
+    full, capped = ToyNet(batch_invariant=True), ToyNet(batch_invariant=True)
+    a = BoxcarOverlapAdd(full, 1, 256, 32, max_batch=None)(x)
+    b = BoxcarOverlapAdd(capped, 1, 256, 32, max_batch=6)(x)
+    assert torch.equal(a, b)
+    assert max(c[0] for c in capped.calls) <= 6 and max(c[0] for c in full.calls) == 2 * 19
+    fullw, cappedw = ToyNet(batch_invariant=True), ToyNet(batch_invariant=True)
+    aw = WindowedOverlapAdd(fullw, 1, 256, 128, reorder_chunks=False, max_batch=None)(x)
+    bw = WindowedOverlapAdd(cappedw, 1, 256, 128, reorder_chunks=False, max_batch=8)(x)
+    assert torch.equal(aw, bw)
+    assert max(c[0] for c in cappedw.calls) <= 8 and len(fullw.calls) == 1
+
+    class TwoSrc:
+        batch_invariant = True
+
+        def __call__(self, t):
+            return {"wav": torch.cat([t, t], dim=1)}
+
+    with pytest.raises(NotImplementedError):
+        WindowedOverlapAdd(TwoSrc(), None, 256, 128)(x)                       # reorder_chunks defaults to True
+    with pytest.raises(NotImplementedError):
+        BoxcarOverlapAdd(TwoSrc(), None, 256, 32, reorder_chunks=True)(x)

@@ -91,7 +91,7 @@ def load_library():
     lib.vf_enable_op_timing.argtypes = [P, c_int]
     lib.vf_op_count.argtypes = [P]
     lib.vf_op_info.argtypes = [P, c_int, POINTER(c_float), POINTER(c_double), POINTER(c_double), POINTER(c_int),
-                               POINTER(c_int), POINTER(c_int), c_char_p, c_int]
+                               POINTER(c_int), POINTER(c_int), c_char_p, c_int, POINTER(c_double)]
     lib.vf_restore_ex.argtypes = [P, P, c_int, c_int64, P, c_uint, P]
     lib.vf_ssr_forward.argtypes = [P, P, P, c_int, c_int64, P, P]
     lib.vf_ssr_restore.argtypes = [P, P, c_int, c_int64, P, P]

@@ -319,9 +319,13 @@ cudaError_t launch_voc_tail(const VocTailParams& p, cudaStream_t stream) {
   dim3 grid((unsigned)((p.L + TAIL_TILE - 1) / TAIL_TILE), p.batch);
   const bool three = p.terms == 3;
   const size_t smem = (size_t)7 * p.C * 4 + (size_t)(three ? 2 : 1) * (TAIL_TILE + 6) * (p.C + 8) * 2;
-  cudaError_t e = three ? cudaFuncSetAttribute(voc_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-                        : cudaFuncSetAttribute(voc_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return e;
+  static bool attr_set[2] = {false, false};     // once per variant (not while a graph is being captured)
+  if (!attr_set[three]) {
+    cudaError_t e = three ? cudaFuncSetAttribute(voc_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                          : cudaFuncSetAttribute(voc_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[three] = true;
+  }
   if (three) voc_tail_kernel<true><<<grid, TAIL_THREADS, smem, stream>>>(p);
   else voc_tail_kernel<false><<<grid, TAIL_THREADS, smem, stream>>>(p);
   return cudaGetLastError();

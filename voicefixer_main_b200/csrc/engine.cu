@@ -77,6 +77,8 @@ struct Op {
   OpKind kind;
   int bn = 0, bk = 0;
   double flops = 0, bytes = 0;   // algorithmic work of this launch (reference op counts), for the roofline
+  double exec_flops = 0;         // tensor-core flops actually issued (3 MMAs per product in 3-term mode, K / phase padding,
+                                 // identity taps): numerator of the "executed" tensor fraction
   char label[48] = {0};
   GemmTcParams tc;
   GemmSimtParams simt;
@@ -134,6 +136,10 @@ struct Plan {
   float* d_sp = nullptr;         // [B, T, 1025] input magnitude
   float* d_mag = nullptr;        // [B, T, 1025] predicted magnitude
   float* d_frames = nullptr;     // [B, T, 2048] windowed inverse-DFT frames
+  // CUDA graphs of the fixed-pointer launch chain (GSR: unet [+ band energy] + vocoder, index = unify flag; SSR: unet),
+  // captured on the second use of the plan (the first runs eagerly and sets the kernels' function attributes)
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  int uses = 0;
   // op slots patched per call
   int fe_op = -1, cond_op = -1, fin_op = -1;
 };
@@ -178,8 +184,10 @@ struct vf_ctx {
   size_t plan_bytes = 0;               // device bytes held by cached plans
   size_t plan_budget = 0;              // cap for plan_bytes (LRU eviction); 0 = decide at first use from free memory
   int64_t plans_evicted = 0;
+  bool use_graphs = true;        // option "graphs"
+  cudaStream_t cap_stream = nullptr;   // capture happens on an internal stream (the caller's may be the legacy default stream)
   bool op_timing = false;
-  struct ProfRec { std::string label; double flops, bytes; int bn, bk, terms; };
+  struct ProfRec { std::string label; double flops, bytes, exec_flops; int bn, bk, terms; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_ev;
   bool timing = false;
@@ -775,16 +783,23 @@ struct Builder {
       tp.prob = pr;
     }
     {   // algorithmic work: the reference op's own MAC count and the minimum HBM traffic of this launch
-      double kreal = 0, a_elems = 0;
+      double kreal = 0;
       for (auto& t : taps) if (!t.both) kreal += (double)t.g * std::min(t.nch, (t.src ? s1 : &s0)->pl.C);
       const double wfrac = (epi.Wp > 1) ? double(epi.Wp - 1) / epi.Wp : 1.0;
       double rows = (double)n_img * (epi.map == MAP_CONVT1D ? epi.rows_in - 1 : epi.rows_in) * wfrac;
       op.flops = 2.0 * rows * N * kreal * (epi.map == MAP_CONVT2D ? 9.0 / 16.0 : 1.0);
-      a_elems += (double)n_img * s0.rows * s0.pl.C;
-      if (s1) a_elems += (double)n_img * s1->rows * s1->pl.C;
+      // bytes per source element: both fp16 planes in 3-term mode, and for a source that an identity tap contracts
+      // with `both` (the hi/lo residual stream of the C <= 128 vocoder stacks); the hi plane alone otherwise
+      bool s1_both = false;
+      for (auto& t : taps) s1_both |= (t.src == 1 && t.both);
+      double a_bytes = (double)n_img * s0.rows * s0.pl.C * (terms == 3 ? 4 : 2);
+      if (s1) a_bytes += (double)n_img * s1->rows * s1->pl.C * ((terms == 3 || s1_both) ? 4 : 2);
+      double kexec = 0;
+      for (auto& t : taps) kexec += (double)t.g * round_up(t.nch, bk) * (terms == 3 ? 3 : (t.both ? 2 : 1));
+      op.exec_flops = 2.0 * (double)n_img * pr.m_tiles * GEMM_BM * N * kexec;
       const double out_elems = (double)n_img * (epi.map == MAP_CONVT1D ? (double)epi.out_rows_valid * epi.cout
                                                 : (epi.map == MAP_CONVT2D ? 4.0 * epi.rows_in * epi.cout : (double)epi.rows_in * N));
-      op.bytes = a_elems * (terms == 3 ? 4 : 2) + (double)W.N * W.K * (terms == 3 ? 4 : 2) +
+      op.bytes = a_bytes + (double)W.N * W.K * (terms == 3 ? 4 : 2) +
                  out_elems * ((epi.out_raw ? 4 : 0) + (epi.out_r.hi ? 4 : 0) + (epi.out_a.hi ? (terms == 3 ? 4 : 2) : 0) + ((epi.resid || epi.resid_hi) ? 4 : 0));
       snprintf(op.label, sizeof op.label, "%s", label.c_str());
     }
@@ -1127,6 +1142,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         pp.slope_out = last ? c.voc_stage_slope : c.voc_res_slope;
         pp.err = ctx->d_err;
         op.flops = 2.0 * 2.0 * (double)B * L * cout * 3.0 * cout;
+        op.exec_flops = 2.0 * 2.0 * (double)B * pp.tiles_per_img * GEMM_BM * cout * 3.0 * cout;
         op.bytes = (double)B * L * cout * (2 + 4 + (last ? 0 : 4) + 2);
         snprintf(op.label, sizeof op.label, "voc.res%d.%d.pair", s, i);
         ops.push_back(op);
@@ -1198,6 +1214,8 @@ int build_ssr(vf_ctx* ctx, Builder& b, Plan* plan) {
 }
 
 void free_plan(Plan* plan) {
+  for (auto& g : plan->graph)
+    if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   for (void* p : plan->allocs) cudaFree(p);
   plan->allocs.clear();
 }
@@ -1324,7 +1342,7 @@ int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
       int rc = prof_mark(ctx, st);
       if (rc) return rc;
       const char* kinds[] = {"gemm", "unet_first", "pool", "voc_condition", "reflect_fill", "voc_tail", "finalize", "memset", "pair"};
-      ctx->prof.push_back({op.label[0] ? std::string(op.label) : std::string(kinds[op.kind]), op.flops, op.bytes, op.bn, op.bk, op.kind == OP_GEMM ? op.tc.prob.terms : 0});
+      ctx->prof.push_back({op.label[0] ? std::string(op.label) : std::string(kinds[op.kind]), op.flops, op.bytes, op.exec_flops, op.bn, op.bk, op.kind == OP_GEMM ? op.tc.prob.terms : 0});
     }
     switch (op.kind) {
       case OP_GEMM:
@@ -1343,6 +1361,47 @@ int run_ops(vf_ctx* ctx, std::vector<Op>& ops, cudaStream_t st) {
     ctx->launches++;
   }
   if (ctx->op_timing) return prof_mark(ctx, st);   // closing event of the last record
+  return VF_OK;
+}
+
+// The middle of a restore - every launch between the front end and the tail kernel - reads and writes plan-owned
+// buffers only, so it is the same work every call: replay it as ONE graph launch instead of ~190 kernel launches
+// (SURVEY.md 7 step 6).  `body` enqueues the chain on a stream; it runs eagerly on the first use of the plan, is
+// captured on the second, and replayed from then on.  Profiling modes always run eagerly.
+template <typename F>
+int run_chain(vf_ctx* ctx, Plan* plan, int slot, cudaStream_t st, int64_t n_launches, F body) {
+  const bool eager = !ctx->use_graphs || ctx->op_timing || ctx->timing || ctx->validate_simt;
+  if (eager || plan->uses++ == 0) return body(st);
+  if (!plan->graph[slot]) {
+    if (!ctx->cap_stream && cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return fail(ctx, VF_ECUDA, "cudaStreamCreate (graph capture) failed");
+    if (cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      return body(st);
+    }
+    const int64_t before = ctx->launches;
+    const int rc = body(ctx->cap_stream);
+    ctx->launches = before;                     // nothing ran yet
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->cap_stream, &g);
+    if (rc || e != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      if (rc) return rc;
+      ctx->use_graphs = false;                  // capture is not available here: stay eager
+      return body(st);
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&plan->graph[slot], g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) {
+      plan->graph[slot] = nullptr;
+      cudaGetLastError();
+      ctx->use_graphs = false;
+      return body(st);
+    }
+  }
+  if (cudaGraphLaunch(plan->graph[slot], st) != cudaSuccess) return fail(ctx, VF_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches += n_launches;
   return VF_OK;
 }
 
@@ -1434,6 +1493,7 @@ VF_API void vf_destroy(vf_ctx* ctx) {
   for (auto& kv : ctx->plans) free_plan(kv.second.get());
   for (void* p : ctx->allocs) cudaFree(p);
   for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
+  if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   delete ctx;
@@ -1527,20 +1587,25 @@ static int restore_impl(vf_ctx* ctx, const float* wav, int batch, int64_t n, flo
   rc = run_frontend(ctx, wav, batch, (long)n, plan->d_mel, plan->d_logmel_in, nullptr, nullptr, nullptr, st);
   if (rc) return rc;
   if (tm) CK(cudaEventRecord(ctx->ev[1], st));
-  rc = run_ops(ctx, plan->unet, st);
-  if (rc) return rc;
-  if (tm) CK(cudaEventRecord(ctx->ev[2], st));
-  {   // eval_gsr_voicefixer.py:54-55: amp_to_original_f when meta["unify_energy"]
+  const bool unify = (flags & VF_RESTORE_UNIFY_ENERGY) != 0;
+  auto chain = [&](cudaStream_t s) -> int {
+    int r = run_ops(ctx, plan->unet, s);
+    if (r) return r;
+    if (tm) CK(cudaEventRecord(ctx->ev[2], s));
+    // eval_gsr_voicefixer.py:54-55: amp_to_original_f when meta["unify_energy"]
     Op& cop = plan->vocoder[plan->cond_op];
+    cop.cond.mel = plan->d_logmel_out;
+    cop.cond.is_log = 1;
     cop.cond.band_sums = nullptr;
-    if (flags & VF_RESTORE_UNIFY_ENERGY) {
-      CK(cudaMemsetAsync(plan->d_band, 0, 2 * (size_t)batch * sizeof(float), st));
-      CK(launch_band_energy(plan->d_mel, plan->d_logmel_out, batch, frames, plan->d_band, st));
+    if (unify) {
+      CK(cudaMemsetAsync(plan->d_band, 0, 2 * (size_t)batch * sizeof(float), s));
+      CK(launch_band_energy(plan->d_mel, plan->d_logmel_out, batch, frames, plan->d_band, s));
       ctx->launches++;
       cop.cond.band_sums = plan->d_band;
     }
-  }
-  rc = run_ops(ctx, plan->vocoder, st);
+    return run_ops(ctx, plan->vocoder, s);
+  };
+  rc = run_chain(ctx, plan, unify ? 1 : 0, st, (int64_t)plan->unet.size() + (int64_t)plan->vocoder.size() + (unify ? 1 : 0), chain);
   if (rc) return rc;
   if (tm) CK(cudaEventRecord(ctx->ev[3], st));
   // eval_gsr_voicefixer.py:68-72: peak normalise + trim_center
@@ -1603,7 +1668,8 @@ static int ssr_impl(vf_ctx* ctx, Plan* plan, const float* sp, const float* wav, 
   }
   if (tm) CK(cudaEventRecord(ctx->ev[1], st));
   plan->unet[0].first.logmel = sp ? sp : plan->d_sp;       // unet_v2.forward(sp, wav): the caller's sp feeds the net
-  rc = run_ops(ctx, plan->unet, st);
+  if (sp) rc = run_ops(ctx, plan->unet, st);               // caller-owned input pointer: not replayable
+  else rc = run_chain(ctx, plan, 0, st, (int64_t)plan->unet.size(), [&](cudaStream_t s) -> int { return run_ops(ctx, plan->unet, s); });
   if (rc) return rc;
   if (tm) CK(cudaEventRecord(ctx->ev[2], st));
   IstftFramesParams fp;
@@ -1821,6 +1887,9 @@ VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value) {
   } else if (k == "validate_simt") {
     slot = &ctx->validate_simt;
     value = value ? 1 : 0;
+  } else if (k == "graphs") {
+    ctx->use_graphs = value != 0;
+    return VF_OK;
   } else if (k == "plan_cache_mb") {
     if (value < 0) return fail(ctx, VF_EINVAL, "plan_cache_mb must be >= 0 (0: half of the free device memory)");
     ctx->plan_budget = (size_t)value << 20;
@@ -1868,7 +1937,8 @@ VF_API int vf_enable_op_timing(vf_ctx* ctx, int enable) {
   return VF_OK;
 }
 VF_API int vf_op_count(vf_ctx* ctx) { return ctx ? (int)ctx->prof.size() : -1; }
-VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, int* terms, char* label, int label_cap) {
+VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* bytes, int* bn, int* bk, int* terms, char* label, int label_cap,
+                      double* exec_flops) {
   if (!ctx || i < 0 || i >= (int)ctx->prof.size()) return VF_EINVAL;
   // records of the frontend / finalize launches are not tracked; record i spans events [i, i+1) except that
   // each run_ops() call appends one closing event after its last op, so consecutive event pairs stay aligned
@@ -1880,6 +1950,7 @@ VF_API int vf_op_info(vf_ctx* ctx, int i, float* ms, double* flops, double* byte
   if (ms) *ms = t;
   if (flops) *flops = ctx->prof[i].flops;
   if (bytes) *bytes = ctx->prof[i].bytes;
+  if (exec_flops) *exec_flops = ctx->prof[i].exec_flops;
   if (bn) *bn = ctx->prof[i].bn;
   if (bk) *bk = ctx->prof[i].bk;
   if (terms) *terms = ctx->prof[i].terms;

@@ -7,7 +7,9 @@ special cases (first chunk has no left margin, last chunk may be short, the sign
 the window).  What differs is the schedule: the reference runs the chunks one by one through `nnet`; here all
 middle chunks of all batch items have the same length and go through `nnet` as ONE batch when the network says it
 is batch-invariant (`nnet.batch_invariant`, true for the B200 engine, whose per-row peak normalisation and
-vocoder are independent across rows) - a 10-minute file becomes a handful of launches of batch ~ 10.
+vocoder are independent across rows), `max_batch` rows at a time: the engine's workspace grows linearly with
+batch x length (~0.14 GB per clip-second), so an unbounded stack of a 20-minute file would not fit a B200, and a
+fixed group size also lets the per-shape plans be reused.  A 10-minute file is three launches of batch 8.
 
 `RestoreNet` adapts `VoiceFixer.restore` to the `nnet(x[B, C, L]) -> {key: [B, n_src, L]}` protocol the class expects.
 """
@@ -41,8 +43,10 @@ class BoxcarOverlapAdd:
     permutation, `:493-495`), which this path does not have: it must be False unless n_src == 1."""
 
     def __init__(self, nnet, n_src: Optional[int], window_size: int, in_margin: int, window=None,
-                 reorder_chunks: bool = False, enable_grad: bool = False, device=None):
+                 reorder_chunks: bool = False, enable_grad: bool = False, device=None, max_batch: Optional[int] = 8):
         assert window_size % 2 == 0, "Window size must be even"          # :396
+        self.max_batch = max_batch                                        # rows per nnet call when chunks are stacked
+        self.reorder_chunks = reorder_chunks
         if in_margin <= 0 or in_margin >= window_size:
             raise ValueError("in_margin must be in (0, window_size)")     # :437-441: the unfold yields n/W chunks only then
         if reorder_chunks and n_src not in (None, 1):
@@ -97,10 +101,13 @@ class BoxcarOverlapAdd:
             if not idx_list:
                 return
             if getattr(self.nnet, "batch_invariant", False) and len(idx_list) > 1:
-                stack = torch.cat([xp[..., chunks[i][0]:chunks[i][1]] for i in idx_list], dim=0)
-                out = self.nnet(stack)[key]
-                for j, i in enumerate(idx_list):
-                    frames[i] = out[j * batch:(j + 1) * batch]
+                per_call = len(idx_list) if not self.max_batch else max(1, self.max_batch // batch)
+                for g0 in range(0, len(idx_list), per_call):
+                    group = idx_list[g0:g0 + per_call]
+                    stack = torch.cat([xp[..., chunks[i][0]:chunks[i][1]] for i in group], dim=0)
+                    out = self.nnet(stack)[key]
+                    for j, i in enumerate(group):
+                        frames[i] = out[j * batch:(j + 1) * batch]
             else:
                 for i in idx_list:
                     frames[i] = self.nnet(xp[..., chunks[i][0]:chunks[i][1]])[key]
@@ -117,6 +124,8 @@ class BoxcarOverlapAdd:
             assert f.ndim == 3, "nnet should return (batch, n_src, time)"  # :477
             if self.n_src is not None:
                 assert f.shape[1] == self.n_src, "nnet should return (batch, n_src, time)"
+            if self.reorder_chunks and f.shape[1] > 1:                      # :493-495 would permute the sources here
+                raise NotImplementedError("reorder_chunks with n_src > 1 (source permutation) is outside this path")
             f = f[..., cl:f.shape[-1] - cr]
             if f.shape[-1] < W:                                             # short last chunk (:461)
                 f = F.pad(f, (0, W - f.shape[-1]))
@@ -139,14 +148,16 @@ class WindowedOverlapAdd:
     """tools/dsp/overlapadd.py:338-484 (`LambdaOverlapAdd`, windowed): the signal is zero-padded by one window on both
     sides, cut into windows of `window_size` every `hop_size` (default half a window), every window goes through
     `nnet`, is multiplied by the synthesis window and overlap-added back (`:419-466`).  All windows have the same
-    length, so a batch-invariant network (the engine) processes the whole file in ONE call.
+    length, so a batch-invariant network (the engine) processes them `max_batch` rows per call.
 
     window: scipy window name ("hanning", the reference's default spelling, is accepted for "hann"), or None/False for
     the unweighted average `frame / (window_size / hop_size)` (`:455-458`)."""
 
     def __init__(self, nnet, n_src: Optional[int], window_size: int, hop_size: Optional[int] = None, window="hanning",
-                 reorder_chunks: bool = True, enable_grad: bool = False, device=None):
+                 reorder_chunks: bool = True, enable_grad: bool = False, device=None, max_batch: Optional[int] = 8):
         assert window_size % 2 == 0, "Window size must be even"          # :392
+        self.max_batch = max_batch                                        # rows per nnet call when windows are stacked
+        self.reorder_chunks = reorder_chunks
         if reorder_chunks and n_src not in (None, 1):
             raise NotImplementedError("source reordering (n_src > 1) is outside this path")
         self.nnet = nnet
@@ -173,7 +184,8 @@ class WindowedOverlapAdd:
         unfolded = unfolded.view(batch, channels, W, n_chunks)              # :431
         if getattr(self.nnet, "batch_invariant", False) and n_chunks > 1:
             stack = unfolded.permute(3, 0, 1, 2).reshape(n_chunks * batch, channels, W).contiguous()
-            frames = self.nnet(stack)[key]
+            rows = stack.shape[0] if not self.max_batch else max(batch, self.max_batch // batch * batch)
+            frames = torch.cat([self.nnet(stack[r0:r0 + rows])[key] for r0 in range(0, stack.shape[0], rows)], dim=0)
             assert frames.ndim == 3, "nnet should return (batch, n_src, time)"
             n_src = frames.shape[1]
             frames = frames.reshape(n_chunks, batch * n_src, W)
@@ -188,6 +200,8 @@ class WindowedOverlapAdd:
             frames = torch.stack(outs)
         if self.n_src is not None:
             assert n_src == self.n_src, "nnet should return (batch, n_src, time)"
+        if self.reorder_chunks and n_src > 1:                               # :446-452 would run _reorder_sources here
+            raise NotImplementedError("reorder_chunks with n_src > 1 (source permutation) is outside this path")
         if self.use_window:
             frames = frames * self.window.to(frames)                        # :455-456
         else:
@@ -204,8 +218,9 @@ class WindowedOverlapAdd:
 
 
 def restore_longform(model, wav: torch.Tensor, window_size: int = 44100 * 30, in_margin: int = 44100 * 2,
-                     unify_energy: bool = False) -> torch.Tensor:
+                     unify_energy: bool = False, max_batch: Optional[int] = 8) -> torch.Tensor:
     """wav [B, N] on the model's device -> [B, N]: VoiceFixer.restore over 30 s windows with 2 s of context on
-    both sides, middle windows batched into one launch chain."""
-    ola = BoxcarOverlapAdd(RestoreNet(model, unify_energy=unify_energy), n_src=1, window_size=window_size, in_margin=in_margin)
+    both sides, middle windows batched `max_batch` rows per launch chain (8 x 34 s = ~38 GB of workspace)."""
+    ola = BoxcarOverlapAdd(RestoreNet(model, unify_energy=unify_energy), n_src=1, window_size=window_size, in_margin=in_margin,
+                           max_batch=max_batch)
     return ola(wav[:, None, :])[:, 0, :]

@@ -350,12 +350,12 @@ class Engine:
         recs = []
         buf = ctypes.create_string_buffer(64)
         for i in range(self.lib.vf_op_count(self.ctx)):
-            ms, fl, by = ctypes.c_float(), ctypes.c_double(), ctypes.c_double()
+            ms, fl, by, ex = ctypes.c_float(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
             bn, bk, tm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
             self._ck(self.lib.vf_op_info(self.ctx, i, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by),
-                                         ctypes.byref(bn), ctypes.byref(bk), ctypes.byref(tm), buf, 64))
+                                         ctypes.byref(bn), ctypes.byref(bk), ctypes.byref(tm), buf, 64, ctypes.byref(ex)))
             recs.append({"label": buf.value.decode(), "ms": ms.value, "flops": fl.value, "bytes": by.value,
-                         "bn": bn.value, "bk": bk.value, "terms": tm.value})
+                         "exec_flops": ex.value, "bn": bn.value, "bk": bk.value, "terms": tm.value})
         return recs
 
     def selftest_gemm(self, n_img, rows, cin, cout, ntaps, dilation=1, terms=3):
