@@ -23,6 +23,9 @@
  *                                 Generator.forward :51-54 -> unet_v2 UNetResComplex_100Mb.forward
  *                                 models/components/unet_v2.py:86-148 (magnitude net, input phase, ISTFT)
  *   vf_istft                      FDomainHelper.istft tools/pytorch/modules/fDomainHelper.py:30-32,127 (torchlibrosa ISTFT)
+ *   vf_resample_poly              load_wav's rate conversion, tools/utils.py:46-48
+ *   vf_lsd / vf_sispec            AudioMetrics.lsd / .sispec evaluation_proc/metrics.py:83-95 (handler's mel metrics,
+ *                                 eval_gsr_voicefixer.py:56-64)
  *
  * Conventions: every function returns 0 on success or a negative VF_E* code and never throws; the message is
  * available from vf_last_error().  All tensor arguments are contiguous fp32.  Unless a name ends in `_host`,
@@ -158,12 +161,28 @@ VF_API int vf_mel(vf_ctx* ctx, const float* specgram, int64_t n_outer, int64_t f
 VF_API int vf_finalize(vf_ctx* ctx, const float* wav, int batch, int64_t len, int64_t n_samples, float* wav_out,
                        void* stream);
 
+/* ---- I/O edges of handler().
+ * Polyphase resampling by up/down (load_wav -> librosa.load(sr=44100), tools/utils.py:46-48, with the arithmetic of
+ * scipy.signal.resample_poly as the reference uses it in tools/dsp/lowpass.py:138-141): out[b,m] = sum_i taps[m*down -
+ * i*up + n_taps/2] * wav[b,i]; taps = the caller's symmetric FIR (odd n_taps, device pointer), n_out = ceil(n*up/down). */
+VF_API int vf_resample_poly(vf_ctx* ctx, const float* wav, int batch, int64_t n_samples, int up, int down, const float* taps,
+                            int n_taps, float* out, int64_t n_out, void* stream);
+/* AudioMetrics.lsd (evaluation_proc/metrics.py:83-87): est, target [images, frames, bins] (non-log) -> out [images]. */
+VF_API int vf_lsd(vf_ctx* ctx, const float* est, const float* target, int images, int frames, int bins, float* out, void* stream);
+/* AudioMetrics.sispec (metrics.py:89-95) per batch item over n values -> out [batch] (the reference then averages over
+ * the batch).  est_map / target_map: 0 none, 1 to_log, 2 from_log applied on the fly (eval_gsr_voicefixer.py:60-62). */
+VF_API int vf_sispec(vf_ctx* ctx, const float* est, const float* target, int batch, int64_t n, int est_map, int target_map,
+                     float* out, void* stream);
+
 VF_API int vf_to_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream);
 VF_API int vf_from_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream);
 /* fp32 samples -> 16-bit PCM exactly as save_wave does it: x * 2^15, truncation toward zero through a 32-bit integer,
  * low 16 bits kept (so +1.0 wraps to -32768 like numpy's astype(np.short) on the reference's hosts).  `out` is a
  * device buffer of n int16. */
 VF_API int vf_to_pcm16(vf_ctx* ctx, const float* in, int16_t* out, int64_t n, void* stream);
+/* saturate != 0: clamp to [-32768, 32767] first, so a peak-normalised +1.0 becomes 32767 instead of wrapping to -32768 (an
+ * audible click the reference's cast produces; not bit-compatible with save_wave, hence opt-in). */
+VF_API int vf_to_pcm16_ex(vf_ctx* ctx, const float* in, int16_t* out, int64_t n, int saturate, void* stream);
 
 /* Device memory the plan for (batch, n_samples) holds (activations + packed weights). */
 VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n_samples, size_t* bytes);

@@ -27,5 +27,10 @@ for spec in $SPECS; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s $((NG+idx)) -c 1 -f \
       -o gpurun_out/prof_$name python tools/profile_step.py --steps 2 > gpurun_out/ncu_$name.log 2>&1
   tail -1 gpurun_out/ncu_$name.log | cut -c1-120
+  # gpurun copies back at most 64 MiB: keep the raw / source pages as CSV, and the binary report of two kernels only
+  ncu -i gpurun_out/prof_$name.ncu-rep --page raw --csv > gpurun_out/prof_${name}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/prof_$name.ncu-rep --page source --csv 2>/dev/null | cut -c1-400 > gpurun_out/prof_${name}_source.csv
+  case $name in voc_res3_1_b|enc1_b2_conv1) ;; *) rm -f gpurun_out/prof_$name.ncu-rep ;; esac
 done
+du -sh gpurun_out
 ls gpurun_out/

@@ -58,18 +58,25 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum"]
-reps = sorted(glob.glob(os.path.join(G, "prof_*.ncu-rep")))
+reps = sorted(set(glob.glob(os.path.join(G, "prof_*.ncu-rep")) + glob.glob(os.path.join(G, "prof_*_raw.csv"))))
+seen = set()
 if reps:
     out += ["## ncu --set full captures (one launch each; `traffic` = dram read + write)", ""]
     table = []
     for rep in reps:
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        name = os.path.basename(rep)[5:-8]
+        if name in seen:
+            continue
+        seen.add(name)
+        if rep.endswith(".csv"):      # exported on the GPU box by tools/run_profile.sh (the binary report stays there)
+            txt = open(rep, errors="ignore").read()
+        else:
+            txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rr = list(csv.reader(txt.splitlines()))
         if len(rr) < 3:
             continue
         hdr, unit, val = rr[0], rr[1], rr[2]
         d = {h: (val[i], unit[i]) for i, h in enumerate(hdr)}
-        name = os.path.basename(rep)[5:-8]
         table.append((name, d))
         with open(os.path.join(P, f"{tag}_{name}_raw.csv"), "w") as f:
             w = csv.writer(f)

@@ -351,16 +351,17 @@ cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream) {
 // tools/file/wav.py:22-24 (save_wave): frames *= 2^15; frames.astype(np.short).  The numpy cast on the reference's
 // x86 hosts truncates toward zero through a 32-bit integer and keeps the low 16 bits, so +1.0 (a peak-normalised
 // maximum) becomes -32768; reproduced bit for bit.
-__global__ void pcm16_kernel(const float* __restrict__ in, int16_t* __restrict__ out, size_t n) {
+__global__ void pcm16_kernel(const float* __restrict__ in, int16_t* __restrict__ out, size_t n, int saturate) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float v = in[i] * 32768.0f;
+    float v = in[i] * 32768.0f;
+    if (saturate) v = fminf(fmaxf(v, -32768.f), 32767.f);       // production option: no wrap of a +1.0 peak
     out[i] = static_cast<int16_t>(static_cast<uint16_t>(static_cast<uint32_t>(__float2int_rz(v)) & 0xffffu));
   }
 }
-cudaError_t launch_pcm16(const float* in, int16_t* out, size_t n, cudaStream_t stream) {
+cudaError_t launch_pcm16(const float* in, int16_t* out, size_t n, int saturate, cudaStream_t stream) {
   const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
-  pcm16_kernel<<<blocks, 256, 0, stream>>>(in, out, n);
+  pcm16_kernel<<<blocks, 256, 0, stream>>>(in, out, n, saturate);
   return cudaGetLastError();
 }
 

@@ -1097,7 +1097,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
     // shared memory.  Its activated input and output planes must differ (a tile reads rows up to `dil` away from
     // the ones another CTA is writing), so the pairs ping-pong between xa and a second plane.
     const bool fused = getenv("VF_TUNE_FUSED_PAIR") && atoi(getenv("VF_TUNE_FUSED_PAIR")) == 1 && !ctx->validate_simt &&
-                       terms == 1 && (cout == 64 || cout == 128);
+                       terms == 1 && cout == 64;
     Planes xa2;
     if (fused) xa2 = b.planes(B, (int)L, cout);
     if (b.rc) return b.rc;
@@ -1127,16 +1127,9 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         pp.out_row0 = (last && last_stage) ? 3 : 0;
         pp.tiles_per_img = (int)((L + 125) / 126);
         const long total_tiles = (long)B * pp.tiles_per_img;
-        int ctas = cout == 64 ? 2 : 1, stages = 0;
-        for (; ctas >= 1; --ctas) {
-          const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
-          for (stages = 8; stages >= 2; --stages)
-            if (pair_tc_smem_bytes(cout, stages) <= per_cta) break;
-          if (stages >= 2) break;
-        }
-        if (ctas < 1 || stages < 2) return fail(ctx, VF_EINVAL, "fused pair: no configuration fits (C=%d)", cout);
-        pp.stages = stages;
-        pp.grid = (int)std::min<long>(total_tiles, (long)ctx->sm_count * ctas);
+        if (pair_tc_smem_bytes(cout, 0) == 0) return fail(ctx, VF_EINVAL, "fused pair: C=%d not built", cout);
+        pp.stages = 2;
+        pp.grid = (int)std::min<long>(total_tiles, (long)ctx->sm_count);      // one persistent CTA per SM (211 KB of shared memory)
         pp.magic_t = gemm_tc_magic((uint32_t)pp.tiles_per_img, (uint64_t)total_tiles);
         pp.slope_h = c.voc_res_slope;
         pp.slope_out = last ? c.voc_stage_slope : c.voc_res_slope;
@@ -1789,6 +1782,34 @@ VF_API int vf_mel(vf_ctx* ctx, const float* specgram, int64_t n_outer, int64_t f
   return VF_OK;
 }
 
+VF_API int vf_resample_poly(vf_ctx* ctx, const float* wav, int batch, int64_t n, int up, int down, const float* taps, int n_taps,
+                            float* out, int64_t n_out, void* stream) {
+  if (!ctx || !wav || !taps || !out || batch <= 0 || n <= 0 || up <= 0 || down <= 0 || n_taps < 1 || (n_taps & 1) == 0)
+    return ctx ? fail(ctx, VF_EINVAL, "vf_resample_poly: bad arguments (n_taps must be odd)") : VF_EINVAL;
+  if (n_out != (n * up + down - 1) / down) return fail(ctx, VF_EINVAL, "vf_resample_poly: n_out must be ceil(n * up / down) = %ld", (long)((n * up + down - 1) / down));
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_resample_poly(wav, batch, (long)n, up, down, taps, n_taps / 2, out, (long)n_out, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+
+VF_API int vf_lsd(vf_ctx* ctx, const float* est, const float* target, int images, int frames, int bins, float* out, void* stream) {
+  if (!ctx || !est || !target || !out || images <= 0 || frames <= 0 || bins <= 0) return ctx ? fail(ctx, VF_EINVAL, "vf_lsd: bad arguments") : VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_lsd(est, target, images, frames, bins, out, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+
+VF_API int vf_sispec(vf_ctx* ctx, const float* est, const float* target, int batch, int64_t n, int est_map, int target_map, float* out, void* stream) {
+  if (!ctx || !est || !target || !out || batch <= 0 || n <= 0 || est_map < 0 || est_map > 2 || target_map < 0 || target_map > 2)
+    return ctx ? fail(ctx, VF_EINVAL, "vf_sispec: bad arguments") : VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_sispec(est, target, batch, (long)n, est_map, target_map, out, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+
 VF_API int vf_finalize(vf_ctx* ctx, const float* wav, int batch, int64_t len, int64_t n, float* wav_out, void* stream) {
   if (!ctx || !wav || !wav_out || batch <= 0 || len <= 0 || n <= 0) return ctx ? fail(ctx, VF_EINVAL, "vf_finalize: bad arguments") : VF_EINVAL;
   const long d = (long)len - (long)n;
@@ -1840,12 +1861,15 @@ VF_API int vf_from_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void
   return VF_OK;
 }
 
-VF_API int vf_to_pcm16(vf_ctx* ctx, const float* in, int16_t* out, int64_t n, void* stream) {
+VF_API int vf_to_pcm16_ex(vf_ctx* ctx, const float* in, int16_t* out, int64_t n, int saturate, void* stream) {
   if (!ctx || !in || !out || n <= 0) return VF_EINVAL;
   CK(cudaSetDevice(ctx->device));
-  CK(launch_pcm16(in, out, (size_t)n, (cudaStream_t)stream));
+  CK(launch_pcm16(in, out, (size_t)n, saturate ? 1 : 0, (cudaStream_t)stream));
   ctx->launches++;
   return VF_OK;
+}
+VF_API int vf_to_pcm16(vf_ctx* ctx, const float* in, int16_t* out, int64_t n, void* stream) {
+  return vf_to_pcm16_ex(ctx, in, out, n, 0, stream);
 }
 
 VF_API int vf_workspace_bytes(vf_ctx* ctx, int batch, int64_t n, size_t* bytes) {

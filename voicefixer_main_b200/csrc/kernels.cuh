@@ -112,7 +112,7 @@ struct FinalizeParams {
   long out_ld, out_off;
 };
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream);
-cudaError_t launch_pcm16(const float* in, int16_t* out, size_t n, cudaStream_t stream);
+cudaError_t launch_pcm16(const float* in, int16_t* out, size_t n, int saturate, cudaStream_t stream);
 
 // max |wav| per clip as float bits (atomicMax), for the stand-alone peak normalise + trim entry point.
 cudaError_t launch_peak(const float* wav, int batch, long L, unsigned int* peak_bits, cudaStream_t stream);
@@ -158,5 +158,11 @@ struct IstftOlaParams {
   long out_ld;
 };
 cudaError_t launch_istft_ola(const IstftOlaParams& p, cudaStream_t stream);
+
+// edges.cu: polyphase resampling (load_wav) and the handler's mel metrics
+cudaError_t launch_resample_poly(const float* x, int batch, long n, int up, int down, const float* h, int half, float* out, long n_out,
+                                 cudaStream_t stream);
+cudaError_t launch_lsd(const float* est, const float* tgt, int images, int T, int F, float* out, cudaStream_t stream);
+cudaError_t launch_sispec(const float* est, const float* tgt, int batch, long n, int est_map, int tgt_map, float* out, cudaStream_t stream);
 
 }  // namespace vf

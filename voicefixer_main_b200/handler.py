@@ -2,9 +2,11 @@
 
 Same signature and contract as the reference handler that evaluation_proc/eval.py:128-132 calls:
     handler(input, output, target, ckpt, device, needrefresh=False, meta={}) -> dict of metrics
-It writes a 16-bit wav at `output`.  Differences, all outside the hot path: audio I/O uses the stdlib `wave`
-module (librosa / soundfile are not in this image, so inputs must already be 44.1 kHz PCM16 wav), and the mel
-metrics that need `target` (evaluation_proc/metrics.py, CPU-side, out of scope) are not computed.
+It writes a 16-bit wav at `output`.  Differences, all outside the hot path: audio decoding uses the stdlib `wave`
+module (librosa / soundfile are not in this image): PCM16 wav of ANY sample rate, converted to 44.1 kHz on the GPU by
+the polyphase resampler (edges.py; load_wav -> librosa.load(sr=44100), tools/utils.py:46-48).  With a `target` the
+per-segment mel metrics of eval_gsr_voicefixer.py:56-64 are computed on the GPU (lsd, sispec, non-log sispec; `mel-ssim`
+is a CPU skimage call in the reference, evaluation_proc/metrics.py:97-106, and is not reported).
 The segment loop, from_log, peak normalisation, trim_center, concat and the int16 conversion of
 tools/file/wav.py:22-24 are reproduced exactly; the per-segment stages run as one fused launch chain.
 """
@@ -20,13 +22,26 @@ hp = None
 SEG_LENGTH = 44100 * 60          # eval_gsr_voicefixer.py:47
 
 
-def load_wav(path, sample_rate=44100):
-    """tools/utils.py:46-48 for PCM16 input at the target rate (no resampling available here)."""
+def read_pcm16(path):
+    """(mono float32 samples in [-1, 1), sample rate) of a 16-bit PCM wav."""
     with wave.open(path, "rb") as w:
-        if w.getframerate() != sample_rate or w.getsampwidth() != 2:
-            raise ValueError(f"{path}: need {sample_rate} Hz 16-bit PCM (got {w.getframerate()} Hz, {8 * w.getsampwidth()} bit)")
+        if w.getsampwidth() != 2:
+            raise ValueError(f"{path}: need 16-bit PCM (got {8 * w.getsampwidth()} bit)")
+        rate = w.getframerate()
         data = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).reshape(-1, w.getnchannels())
-    return (data.astype(np.float32) / 32768.0).mean(axis=1).astype(np.float32)
+    return (data.astype(np.float32) / 32768.0).mean(axis=1).astype(np.float32), rate
+
+
+def load_wav(path, sample_rate=44100, engine=None):
+    """tools/utils.py:46-48 (librosa.load(path, sr=sample_rate)): decode + convert to `sample_rate`.  Rate conversion
+    runs on the GPU (`engine`, edges.resample_to); a file already at the target rate needs no engine."""
+    wav, rate = read_pcm16(path)
+    if rate == sample_rate:
+        return wav
+    if engine is None:
+        raise ValueError(f"{path}: {rate} Hz input needs an engine for the GPU resampler (pass engine=model._engine())")
+    from .edges import resample_to
+    return resample_to(engine, torch.from_numpy(wav)[None].to(engine.device), rate, sample_rate)[0].cpu().numpy()
 
 
 def save_wave(frames: np.ndarray, fname, sample_rate=44100):
@@ -57,8 +72,11 @@ def refresh_model(ckpt):
     model.eval()
 
 
-def restore_array(mdl: VoiceFixer, wav_10k: np.ndarray, device, unify_energy: bool = False) -> torch.Tensor:
-    """The segment loop of handler() for one in-memory file: returns [1, N] on `device`."""
+def restore_array(mdl: VoiceFixer, wav_10k: np.ndarray, device, unify_energy: bool = False, target: np.ndarray = None,
+                  metrics: dict = None) -> torch.Tensor:
+    """The segment loop of handler() for one in-memory file: returns [1, N] on `device`.  With `target` (the clean
+    signal, same rate) the mel metrics of the LAST segment land in `metrics`, as the reference's loop leaves them
+    (eval_gsr_voicefixer.py:56-64 overwrites the dict every segment)."""
     res = []
     break_point = SEG_LENGTH
     n = wav_10k.shape[0]
@@ -66,6 +84,23 @@ def restore_array(mdl: VoiceFixer, wav_10k: np.ndarray, device, unify_energy: bo
         segment = wav_10k[break_point - SEG_LENGTH:break_point]
         seg = torch.from_numpy(np.ascontiguousarray(segment))[None, :].to(device)
         res.append(mdl.restore(seg, unify_energy=unify_energy))
+        if target is not None and metrics is not None:
+            from .edges import AudioMetrics
+            am = AudioMetrics(mdl)
+            eng = mdl._engine()
+            tseg = torch.from_numpy(np.ascontiguousarray(target[break_point - SEG_LENGTH:break_point]))[None, None, :].to(device)
+            _, target_mel = mdl.pre(tseg)
+            mel_noisy, log_mel = eng.restore_stages(1, seg.shape[1])
+            log_mel, mel_noisy = log_mel[:, None], mel_noisy[:, None]
+            denoised = eng.from_log(log_mel)
+            if unify_energy:                     # eval_gsr_voicefixer.py:54-55 (tools/utils.py:50-55) before the lsd
+                lo = slice(5, int(128 * 0.2))
+                denoised = denoised * (mel_noisy[..., lo].mean(dim=(2, 3)) / denoised[..., lo].mean(dim=(2, 3)))[..., None, None]
+            metrics.update({
+                "mel-lsd": float(am.lsd(denoised.contiguous(), target_mel.contiguous())),
+                "mel-sispec": float(am.sispec(log_mel, target_mel.contiguous(), target_map=1)),             # in log scale
+                "mel-non-log-sispec": float(am.sispec(log_mel, target_mel.contiguous(), est_map=2)),
+            })
         break_point += SEG_LENGTH
     return torch.cat(res, -1)
 
@@ -76,9 +111,12 @@ def handler(input, output, target, ckpt, device, needrefresh=False, meta={}):
     global model
     model = model.to(device)
     metrics = {}
-    wav_10k = load_wav(input, sample_rate=44100)
-    out = restore_array(model, wav_10k, model.device, unify_energy=bool(meta.get("unify_energy", False)))
+    wav_10k = load_wav(input, sample_rate=44100, engine=model._engine())
+    tgt = load_wav(target, sample_rate=44100, engine=model._engine()) if target is not None else None
+    out = restore_array(model, wav_10k, model.device, unify_energy=bool(meta.get("unify_energy", False)), target=tgt, metrics=metrics)
     # save_wave's float -> int16 conversion runs on the GPU (its `max <= 1` condition always holds after the
-    # per-segment peak normalisation), so only 2 bytes per sample cross PCIe
-    save_pcm16(model._engine().to_pcm16(out[0]).cpu().numpy(), fname=output, sample_rate=44100)
+    # per-segment peak normalisation), so only 2 bytes per sample cross PCIe.  meta["saturate"] (not in the reference)
+    # clamps instead of reproducing numpy's +1.0 -> -32768 wrap, see INTEGRATION.md
+    pcm = model._engine().to_pcm16(out[0], saturate=bool(meta.get("saturate", False)))
+    save_pcm16(pcm.cpu().numpy(), fname=output, sample_rate=44100)
     return metrics

@@ -306,12 +306,13 @@ class Engine:
             self._ck(self.lib.vf_from_log(self.ctx, _ptr(x), _ptr(out), x.numel(), _stream()))
         return out
 
-    def to_pcm16(self, x):
-        """fp32 samples -> int16 PCM exactly as save_wave (tools/file/wav.py:22-24) converts them."""
+    def to_pcm16(self, x, saturate: bool = False):
+        """fp32 samples -> int16 PCM exactly as save_wave (tools/file/wav.py:22-24) converts them; saturate=True clamps
+        instead of wrapping +1.0 to -32768 (not bit-compatible with the reference)."""
         x = _check_in(x, self.device, "input")
         out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
         with torch.cuda.device(self.device):
-            self._ck(self.lib.vf_to_pcm16(self.ctx, _ptr(x), _ptr(out), x.numel(), _stream()))
+            self._ck(self.lib.vf_to_pcm16_ex(self.ctx, _ptr(x), _ptr(out), x.numel(), int(saturate), _stream()))
         return out
 
     def check_errors(self):
