@@ -128,8 +128,11 @@ VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n_sample
                                         meta["unify_energy"] is set, eval_gsr_voicefixer.py:54-55 */
 VF_API int vf_restore_ex(vf_ctx* ctx, const float* wav, int batch, int64_t n_samples, float* wav_out, unsigned flags,
                          void* stream);
-/* Same through HOST buffers (pinned for true asynchrony): H2D copy, vf_restore, D2H copy on `stream`.
- * The caller synchronises the stream before reading out_host. */
+/* Same through HOST buffers (pinned for true asynchrony).  The copies and the compute run on library-owned streams with
+ * two staging buffer pairs, so back-to-back calls overlap (the H2D of call i+1 and the D2H of call i-1 run under the
+ * compute of call i); `stream` only receives a wait on this call's D2H.  Contract: wav_host holds its data when the
+ * call is made (host-written; it is not ordered after work queued on `stream`), and the caller synchronises `stream`
+ * before reading out_host or reusing wav_host.  Option "host_pipeline" = 0 restores the single-stream behaviour. */
 VF_API int vf_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_t n_samples, float* out_host, void* stream);
 /* Copies the intermediate results of the last vf_restore of this (batch, n_samples) into caller buffers
  * [B,T,128] (either may be NULL): the linear mel of stage A and the restored log10 mel of stage B. */
@@ -193,6 +196,8 @@ VF_API int vf_check_errors(vf_ctx* ctx, void* stream);
 /* Options: "vocoder_terms" (1 or 3 fp16 split terms; "unet_terms" accepts only 3), "unify_energy" (default flag of
  * vf_restore / vf_restore_host; prefer vf_restore_ex's per-call flag), "plan_cache_mb" (cap on the device memory
  * held by cached per-shape plans, least recently used evicted first; 0 = half of the free device memory),
+ * "graphs" (default 1: the fixed-pointer launch chain of a plan is captured on its second use and replayed as one CUDA graph from then on),
+ * "host_pipeline" (default 1, see vf_restore_host),
  * "validate_simt" (1: run every GEMM on the SIMT validation kernel instead of tcgen05 - tests only). */
 VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value);
 /* Plans are cached per (path, batch, frames); the cache is bounded (see "plan_cache_mb"). */

@@ -123,8 +123,15 @@ struct Plan {
   std::vector<void*> allocs;
   size_t bytes = 0;
   std::vector<Op> frontend, unet, vocoder, tail;
-  float* d_wav = nullptr;        // [B, N]   staged input (restore_host)
+  float* d_wav = nullptr;        // [B, N]   staged input of the host entry points (buffer 0)
   float* d_out = nullptr;        // [B, N]
+  float* d_io[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][in / out]: double-buffered host staging
+  cudaEvent_t io_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // h2d done, input consumed, compute done, d2h done
+  unsigned io_seq = 0;
+  // a plan's buffers are shared by every call of its shape: uses on different streams are ordered through this event
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
   float* d_mel = nullptr;        // [B, T, 128] linear mel
   float* d_logmel_in = nullptr;  // [B, T, 128] log10 mel (UNet input)
   float* d_logmel_out = nullptr; // [B, T, 128]
@@ -186,6 +193,10 @@ struct vf_ctx {
   int64_t plans_evicted = 0;
   bool use_graphs = true;        // option "graphs"
   cudaStream_t cap_stream = nullptr;   // capture happens on an internal stream (the caller's may be the legacy default stream)
+  // host entry points: copies and compute on internal streams, so the H2D of call i+1 and the D2H of call i-1 overlap the
+  // compute of call i (option "host_pipeline"); the caller's stream only waits for the call's own D2H
+  bool host_pipeline = true;
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   bool op_timing = false;
   struct ProfRec { std::string label; double flops, bytes, exec_flops; int bn, bk, terms; };
   std::vector<ProfRec> prof;
@@ -1209,6 +1220,10 @@ int build_ssr(vf_ctx* ctx, Builder& b, Plan* plan) {
 void free_plan(Plan* plan) {
   for (auto& g : plan->graph)
     if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  for (auto& row : plan->io_ev)
+    for (auto& e : row)
+      if (e) { cudaEventDestroy(e); e = nullptr; }
+  if (plan->ev_last) { cudaEventDestroy(plan->ev_last); plan->ev_last = nullptr; }
   for (void* p : plan->allocs) cudaFree(p);
   plan->allocs.clear();
 }
@@ -1310,11 +1325,68 @@ int ensure_io(vf_ctx* ctx, Plan* plan, long n) {
   if (plan->n_samples >= n && plan->d_wav) return VF_OK;
   const size_t before = plan->bytes;
   Builder b{ctx, plan};
-  plan->d_wav = b.alloc<float>((size_t)plan->batch * n);
-  plan->d_out = b.alloc<float>((size_t)plan->batch * n);
+  for (int k = 0; k < 2; ++k) {
+    plan->d_io[k][0] = b.alloc<float>((size_t)plan->batch * n);
+    plan->d_io[k][1] = b.alloc<float>((size_t)plan->batch * n);
+  }
+  plan->d_wav = plan->d_io[0][0];
+  plan->d_out = plan->d_io[0][1];
   plan->n_samples = n;
   ctx->plan_bytes += plan->bytes - before;
   return b.rc;
+}
+
+// Orders this use of the plan's buffers after the previous one when that ran on another stream.
+int plan_enter(vf_ctx* ctx, Plan* plan, cudaStream_t st) {
+  if (plan->used && plan->last_stream != st) CK(cudaStreamWaitEvent(st, plan->ev_last, 0));
+  return VF_OK;
+}
+int plan_exit(vf_ctx* ctx, Plan* plan, cudaStream_t st) {
+  if (!plan->ev_last) CK(cudaEventCreateWithFlags(&plan->ev_last, cudaEventDisableTiming));
+  CK(cudaEventRecord(plan->ev_last, st));
+  plan->last_stream = st;
+  plan->used = true;
+  return VF_OK;
+}
+
+// Host-buffer round trip around `body(d_in, d_out, stream)`.  Pipelined mode: H2D on s_in, compute on s_comp, D2H on
+// s_out, two staging buffer pairs; consecutive calls overlap (copy-in of the next, copy-out of the previous) and the
+// caller's stream waits only for this call's D2H, so synchronising it still means "out_host is complete".
+template <typename F>
+int host_roundtrip(vf_ctx* ctx, Plan* plan, const float* in_host, float* out_host, size_t bytes, cudaStream_t st, F body) {
+  if (!ctx->host_pipeline) {
+    CK(cudaMemcpyAsync(plan->d_wav, in_host, bytes, cudaMemcpyHostToDevice, st));
+    int rc = body(plan->d_wav, plan->d_out, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_host, plan->d_out, bytes, cudaMemcpyDeviceToHost, st));
+    return VF_OK;
+  }
+  if (!ctx->s_in) {
+    CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  }
+  const int k = (int)(plan->io_seq++ & 1u);
+  cudaEvent_t* ev = plan->io_ev[k];
+  for (int i = 0; i < 4; ++i)
+    if (!ev[i]) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  float* d_in = plan->d_io[k][0];
+  float* d_out = plan->d_io[k][1];
+  // (waiting on an event that was never recorded is a no-op)
+  CK(cudaStreamWaitEvent(ctx->s_in, ev[1], 0));                 // the compute that read this input buffer two calls ago
+  CK(cudaMemcpyAsync(d_in, in_host, bytes, cudaMemcpyHostToDevice, ctx->s_in));
+  CK(cudaEventRecord(ev[0], ctx->s_in));
+  CK(cudaStreamWaitEvent(ctx->s_comp, ev[0], 0));
+  CK(cudaStreamWaitEvent(ctx->s_comp, ev[3], 0));               // the D2H that read this output buffer two calls ago
+  int rc = body(d_in, d_out, ctx->s_comp);
+  if (rc) return rc;
+  CK(cudaEventRecord(ev[1], ctx->s_comp));
+  CK(cudaEventRecord(ev[2], ctx->s_comp));
+  CK(cudaStreamWaitEvent(ctx->s_out, ev[2], 0));
+  CK(cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+  CK(cudaEventRecord(ev[3], ctx->s_out));
+  CK(cudaStreamWaitEvent(st, ev[3], 0));
+  return VF_OK;
 }
 
 int prof_mark(vf_ctx* ctx, cudaStream_t st) {
@@ -1487,6 +1559,8 @@ VF_API void vf_destroy(vf_ctx* ctx) {
   for (void* p : ctx->allocs) cudaFree(p);
   for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
   if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+  for (cudaStream_t st : {ctx->s_in, ctx->s_comp, ctx->s_out})
+    if (st) cudaStreamDestroy(st);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   delete ctx;
@@ -1532,12 +1606,14 @@ VF_API int vf_unet_mel(vf_ctx* ctx, const float* mel_lin, int batch, int frames,
   rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
   const size_t n = (size_t)batch * frames * 128;
+  rc = plan_enter(ctx, plan, st);
+  if (rc) return rc;
   CK(launch_to_log(mel_lin, plan->d_logmel_in, n, ctx->d_err + 1, st));
   ctx->launches++;
   rc = run_ops(ctx, plan->unet, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(logmel_out, plan->d_logmel_out, n * 4, cudaMemcpyDeviceToDevice, st));
-  return VF_OK;
+  return plan_exit(ctx, plan, st);
 }
 
 VF_API int64_t vf_vocoder_out_len(vf_ctx* ctx, int frames) {
@@ -1553,6 +1629,8 @@ VF_API int vf_vocoder(vf_ctx* ctx, const float* mel_lin, int batch, int frames, 
   Plan* plan;
   rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
+  rc = plan_enter(ctx, plan, st);
+  if (rc) return rc;
   Op& cop = plan->vocoder[plan->cond_op];
   cop.cond.mel = mel_lin;
   cop.cond.is_log = 0;
@@ -1562,7 +1640,7 @@ VF_API int vf_vocoder(vf_ctx* ctx, const float* mel_lin, int batch, int frames, 
   cop.cond.is_log = 1;
   if (rc) return rc;
   CK(cudaMemcpyAsync(wav_out, plan->d_voc_wav, (size_t)batch * plan->L * 4, cudaMemcpyDeviceToDevice, st));
-  return VF_OK;
+  return plan_exit(ctx, plan, st);
 }
 
 static int restore_impl(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, unsigned flags, cudaStream_t st) {
@@ -1571,6 +1649,8 @@ static int restore_impl(vf_ctx* ctx, const float* wav, int batch, int64_t n, flo
   int rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
   if (ctx->op_timing) ctx->prof.clear();
+  rc = plan_enter(ctx, plan, st);
+  if (rc) return rc;
   const bool tm = ctx->timing;
   if (tm) {
     for (auto& e : ctx->ev)
@@ -1611,7 +1691,7 @@ static int restore_impl(vf_ctx* ctx, const float* wav, int batch, int64_t n, flo
   CK(launch_finalize(f, st));
   ctx->launches++;
   if (tm) { CK(cudaEventRecord(ctx->ev[4], st)); ctx->ev_valid = true; }
-  return VF_OK;
+  return plan_exit(ctx, plan, st);
 }
 
 VF_API int vf_restore_ex(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, unsigned flags, void* stream) {
@@ -1636,25 +1716,23 @@ VF_API int vf_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_
   if (rc) return rc;
   rc = ensure_io(ctx, plan, (long)n);
   if (rc) return rc;
-  const size_t bytes = (size_t)batch * n * 4;
-  CK(cudaMemcpyAsync(plan->d_wav, wav_host, bytes, cudaMemcpyHostToDevice, st));
-  rc = restore_impl(ctx, plan->d_wav, batch, n, plan->d_out, ctx->unify_energy ? VF_RESTORE_UNIFY_ENERGY : 0u, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out_host, plan->d_out, bytes, cudaMemcpyDeviceToHost, st));
-  return VF_OK;
+  const unsigned flags = ctx->unify_energy ? VF_RESTORE_UNIFY_ENERGY : 0u;
+  return host_roundtrip(ctx, plan, wav_host, out_host, (size_t)batch * n * 4, st,
+                        [&](const float* d_in, float* d_out, cudaStream_t s) { return restore_impl(ctx, d_in, batch, n, d_out, flags, s); });
 }
 
 // ---------------------------------------------------------------------------------------------- SSR / GSR-UNet path
 static int ssr_impl(vf_ctx* ctx, Plan* plan, const float* sp, const float* wav, int batch, int64_t n, float* wav_out, cudaStream_t st) {
   const int frames = plan->T;
   if (ctx->op_timing) ctx->prof.clear();
+  int rc = plan_enter(ctx, plan, st);
+  if (rc) return rc;
   const bool tm = ctx->timing;
   if (tm) {
     for (auto& e : ctx->ev)
       if (!e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(ctx->ev[0], st));
   }
-  int rc = VF_OK;
   if (!sp) {     // SSR_UNet.pre (ssr_unet.py:140-143): the magnitude of the input itself
     rc = run_frontend(ctx, wav, batch, (long)n, nullptr, nullptr, plan->d_sp, nullptr, nullptr, st);
     if (rc) return rc;
@@ -1677,7 +1755,7 @@ static int ssr_impl(vf_ctx* ctx, Plan* plan, const float* sp, const float* wav, 
   CK(launch_istft_ola(op, st));
   ctx->launches += 2;
   if (tm) { CK(cudaEventRecord(ctx->ev[3], st)); CK(cudaEventRecord(ctx->ev[4], st)); ctx->ev_valid = true; }
-  return VF_OK;
+  return plan_exit(ctx, plan, st);
 }
 
 VF_API int vf_ssr_forward(vf_ctx* ctx, const float* sp, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
@@ -1706,12 +1784,8 @@ VF_API int vf_ssr_restore_host(vf_ctx* ctx, const float* wav_host, int batch, in
   if (rc) return rc;
   rc = ensure_io(ctx, plan, (long)n);
   if (rc) return rc;
-  const size_t bytes = (size_t)batch * n * 4;
-  CK(cudaMemcpyAsync(plan->d_wav, wav_host, bytes, cudaMemcpyHostToDevice, st));
-  rc = ssr_impl(ctx, plan, nullptr, plan->d_wav, batch, n, plan->d_out, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out_host, plan->d_out, bytes, cudaMemcpyDeviceToHost, st));
-  return VF_OK;
+  return host_roundtrip(ctx, plan, wav_host, out_host, (size_t)batch * n * 4, st,
+                        [&](const float* d_in, float* d_out, cudaStream_t s) { return ssr_impl(ctx, plan, nullptr, d_in, batch, n, d_out, s); });
 }
 
 VF_API int vf_ssr_unet(vf_ctx* ctx, const float* sp, int batch, int frames, float* mag_out, void* stream) {
@@ -1723,11 +1797,13 @@ VF_API int vf_ssr_unet(vf_ctx* ctx, const float* sp, int batch, int frames, floa
   rc = get_plan(ctx, PLAN_SSR, batch, frames, &plan);
   if (rc) return rc;
   if (ctx->op_timing) ctx->prof.clear();
+  rc = plan_enter(ctx, plan, st);
+  if (rc) return rc;
   plan->unet[0].first.logmel = sp;
   rc = run_ops(ctx, plan->unet, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(mag_out, plan->d_mag, (size_t)batch * frames * 1025 * 4, cudaMemcpyDeviceToDevice, st));
-  return VF_OK;
+  return plan_exit(ctx, plan, st);
 }
 
 VF_API int vf_ssr_stages(vf_ctx* ctx, int batch, int64_t n, float* sp_out, float* mag_out, void* stream) {
@@ -1738,9 +1814,11 @@ VF_API int vf_ssr_stages(vf_ctx* ctx, int batch, int64_t n, float* sp_out, float
   rc = get_plan(ctx, PLAN_SSR, batch, frames, &plan);
   if (rc) return rc;
   const size_t bytes = (size_t)batch * frames * 1025 * 4;
+  rc = plan_enter(ctx, plan, (cudaStream_t)stream);
+  if (rc) return rc;
   if (sp_out) CK(cudaMemcpyAsync(sp_out, plan->d_sp, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (mag_out) CK(cudaMemcpyAsync(mag_out, plan->d_mag, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  return VF_OK;
+  return plan_exit(ctx, plan, (cudaStream_t)stream);
 }
 
 VF_API int vf_istft(vf_ctx* ctx, const float* real, const float* imag, int batch, int frames, int64_t length, float* wav_out, void* stream) {
@@ -1841,9 +1919,11 @@ VF_API int vf_restore_stages(vf_ctx* ctx, int batch, int64_t n, float* mel_lin_o
   rc = get_plan(ctx, PLAN_GSR, batch, frames, &plan);
   if (rc) return rc;
   const size_t bytes = (size_t)batch * frames * 128 * 4;
+  rc = plan_enter(ctx, plan, (cudaStream_t)stream);
+  if (rc) return rc;
   if (mel_lin_out) CK(cudaMemcpyAsync(mel_lin_out, plan->d_mel, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (log_mel_out) CK(cudaMemcpyAsync(log_mel_out, plan->d_logmel_out, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  return VF_OK;
+  return plan_exit(ctx, plan, (cudaStream_t)stream);
 }
 
 VF_API int vf_to_log(vf_ctx* ctx, const float* in, float* out, int64_t n, void* stream) {
@@ -1911,6 +1991,11 @@ VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value) {
   } else if (k == "validate_simt") {
     slot = &ctx->validate_simt;
     value = value ? 1 : 0;
+  } else if (k == "host_pipeline") {
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->host_pipeline = value != 0;
+    return VF_OK;
   } else if (k == "graphs") {
     ctx->use_graphs = value != 0;
     return VF_OK;
