@@ -1086,8 +1086,15 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
     const int sc = c.voc_scales[s], cout = cin / 2;
     const long L = Lprev * sc;
     const bool last_stage = s == c.voc_num_stages - 1;
-    Planes xr[2] = {b.planes(B, (int)L, cout), b.planes(B, (int)L, cout)};   // residual stream x as hi/lo planes
-    Planes xa = b.planes(B, (int)L, cout), ha = b.planes(B, (int)L, cout);
+    // C = 64 stacks in the hi-only mode: one kernel per residual pair (pair_tc.cu), the intermediate h stays in shared
+    // memory and the residual stream of the stack is fp32.  Measured 2.33 vs 2.49 ms per pair against the two GEMM launches
+    // (B = 32 x 10 s); VF_TUNE_FUSED_PAIR=0 selects the two-launch path.  Its activated input and output planes must differ
+    // (a tile reads rows up to `dil` away from the ones another CTA is writing), so the pairs ping-pong between xa and xa2.
+    const char* fenv = getenv("VF_TUNE_FUSED_PAIR");
+    const bool fused = !(fenv && atoi(fenv) == 0) && !ctx->validate_simt && terms == 1 && cout == 64;
+    // residual stream x as hi/lo planes (ping-pong; a fused stack only reads the first, written by the transposed conv)
+    Planes xr[2] = {b.planes(B, (int)L, cout), fused ? Planes() : b.planes(B, (int)L, cout)};
+    Planes xa = b.planes(B, (int)L, cout), ha = fused ? Planes() : b.planes(B, (int)L, cout);
     Planes tail_in;
     if (last_stage) tail_in = b.planes(B, (int)L + 6, cout);
     if (b.rc) return b.rc;
@@ -1104,13 +1111,13 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
       b.gemm(ops, ctx->voc_up[s], ASrc{prev, (int)Lprev, 0}, nullptr, taps, e, B, terms);
     }
     int curx = 0;
-    // EXPERIMENTAL, opt-in (VF_TUNE_FUSED_PAIR=1): one kernel per residual pair (pair_tc.cu), the intermediate stays in
-    // shared memory.  Its activated input and output planes must differ (a tile reads rows up to `dil` away from
-    // the ones another CTA is writing), so the pairs ping-pong between xa and a second plane.
-    const bool fused = getenv("VF_TUNE_FUSED_PAIR") && atoi(getenv("VF_TUNE_FUSED_PAIR")) == 1 && !ctx->validate_simt &&
-                       terms == 1 && cout == 64;
     Planes xa2;
-    if (fused) xa2 = b.planes(B, (int)L, cout);
+    float* xf[2] = {nullptr, nullptr};       // fp32 residual stream of a fused stack (ping-pong)
+    if (fused) {
+      xa2 = b.planes(B, (int)L, cout);
+      xf[0] = b.alloc<float>((size_t)B * L * cout);
+      xf[1] = b.alloc<float>((size_t)B * L * cout);
+    }
     if (b.rc) return b.rc;
     int cura = 0;
     for (int i = 0; i < c.voc_depth[s]; ++i) {
@@ -1130,8 +1137,9 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         if (mrc) return mrc;
         pp.bias_a = ctx->voc_res_a[s][i].bias;
         pp.bias_b = ctx->voc_res_b[s][i].bias;
-        pp.resid_hi = xr[curx].p.hi; pp.resid_lo = xr[curx].p.lo;
-        if (!last) { pp.out_r_hi = xr[1 - curx].p.hi; pp.out_r_lo = xr[1 - curx].p.lo; }
+        if (i == 0) { pp.resid_hi = xr[0].p.hi; pp.resid_lo = xr[0].p.lo; }      // written by the transposed conv above
+        else pp.resid_f32 = xf[curx];
+        if (!last) pp.out_f32 = xf[1 - curx];
         pp.out_a = dst.p.hi;
         pp.L = (int)L; pp.n_img = B; pp.C = cout; pp.dil = dil;
         pp.out_img_rows = dst.img_rows;
@@ -1147,7 +1155,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         pp.err = ctx->d_err;
         op.flops = 2.0 * 2.0 * (double)B * L * cout * 3.0 * cout;
         op.exec_flops = 2.0 * 2.0 * (double)B * pp.tiles_per_img * GEMM_BM * cout * 3.0 * cout;
-        op.bytes = (double)B * L * cout * (2 + 4 + (last ? 0 : 4) + 2);
+        op.bytes = (double)B * L * cout * (2 + 4 + (last ? 0 : 4) + 2);      // act in, x in, x_new out, act out
         snprintf(op.label, sizeof op.label, "voc.res%d.%d.pair", s, i);
         ops.push_back(op);
         curx = 1 - curx;

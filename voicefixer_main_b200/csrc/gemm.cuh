@@ -120,10 +120,10 @@ struct PairParams {
   CUtensorMap wa_map, wb_map;    // packed K-major hi weights [K >= 3C, C], box 64 x C
   const float* bias_a;
   const float* bias_b;
-  const __half* resid_hi;        // x, hi/lo planes [clips, L, C]
+  const __half* resid_hi;        // x as hi/lo planes [clips, L, C] (first pair of a stack: written by the up-sampling GEMM) ...
   const __half* resid_lo;
-  __half* out_r_hi;              // x_new raw planes (null for the last pair of a stage)
-  __half* out_r_lo;
+  const float* resid_f32;        // ... or as the stack's fp32 stream [clips, L, C] (non-null selects it)
+  float* out_f32;                // x_new, fp32 stream (null for the last pair of a stage)
   __half* out_a;                 // lrelu(x_new, slope_out), hi plane [clips, out_img_rows, C], first row out_row0
   int L, n_img, C, dil, out_img_rows, out_row0, tiles_per_img, stages, grid;
   uint32_t magic_t;              // gemm_tc_magic(tiles_per_img, ...)

@@ -23,7 +23,8 @@
 //   warp 1       MMA issuer, software pipelined P1(j+1) before P2(j); 12 MMAs per barrier round trip, descriptors
 //                precomputed per stage (the issue thread's per-chunk instruction count bounds narrow tiles)
 //   warps 2-5    E1: accumulator 1 -> H (two H buffers)
-//   warps 6-13   E2: residual planes prefetched into registers BEFORE the accumulator wait, accumulator 2 -> global
+//   warps 6-13   E2: residual (fp32 stream of the stack; hi/lo planes for its first pair) prefetched one tile ahead,
+//                accumulator 2 -> fp32 x_new + the activated fp16 plane of the next pair
 // Every wait is bounded (ptx.cuh).
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -43,6 +44,7 @@ constexpr int PAIR_THREADS = 64 + PAIR_E1_THREADS + PAIR_E2_THREADS;
 constexpr int PAIR_SMEM = 2 * PAIR_A_STAGE + 6 * PAIR_W_TAP + 2 * PAIR_H_BUF + PAIR_E2_WARPS * 4096 + 256 + 2 * PAIR_C * 4 + 1024;
 }  // namespace
 
+template <bool F32_IN>
 __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_constant__ PairParams P) {
   constexpr int C = PAIR_C;
   constexpr uint32_t IDESC = make_idesc_f16(GEMM_BM, C);
@@ -172,6 +174,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
     const float slope_h = P.slope_h;
     float amax = 0.f;
     bool ok = true;
+    // buffer rows 0 and 129 of both H buffers are read by the first / last tap of accumulator rows 0 and 127 (never stored,
+    // but they must stay finite for the overflow guard): zero them once, E1 only ever writes rows 1..128
+    if (warp == 2 && lane < 16) {
+      uint8_t* hb = h_base + (size_t)(lane >> 3) * PAIR_H_BUF;
+      *reinterpret_cast<uint4*>(hb + (lane & 7) * 16) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(hb + 129 * 128 + (lane & 7) * 16) = make_uint4(0, 0, 0, 0);
+    }
     for (int j = 0; j < n_local && ok; ++j) {
       const int tile = blockIdx.x + j * gridDim.x;
       const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
@@ -182,21 +191,22 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
       const bool in_clip = t >= 0 && t < P.L;
       if (!mbar_wait(acc1_full + b, pj, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       tc_fence_after();
-      float v[2][32];
-      tmem_ld_32x32(tmem_base + lane_bits + b * C, v[0]);
-      tmem_ld_32x32(tmem_base + lane_bits + b * C + 32, v[1]);
-      tc_fence_before();
-      mbar_arrive(acc1_empty + b);             // accumulator 1[b] is in registers: P1(j+2) may start
       if (!mbar_wait(h_free + b, pj ^ 1u, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }   // P2(j-2) has read H[b]
       uint8_t* rowp = h_base + (size_t)b * PAIR_H_BUF + (size_t)brow * 128;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {              // two passes of 32 columns
+        float v[32];
+        tmem_ld_32x32(tmem_base + lane_bits + b * C + c * 32, v);
+        if (c == 1) {
+          tc_fence_before();
+          mbar_arrive(acc1_empty + b);           // accumulator 1[b] is in registers: P1(j+2) may start
+        }
         const float4* bp = reinterpret_cast<const float4*>(s_bias_a + c * 32);
         uint32_t hw[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 b4 = bp[i];
-          float a0 = v[c][4 * i] + b4.x, a1 = v[c][4 * i + 1] + b4.y, a2 = v[c][4 * i + 2] + b4.z, a3 = v[c][4 * i + 3] + b4.w;
+          float a0 = v[4 * i] + b4.x, a1 = v[4 * i + 1] + b4.y, a2 = v[4 * i + 2] + b4.z, a3 = v[4 * i + 3] + b4.w;
           a0 = fmaxf(a0, a0 * slope_h); a1 = fmaxf(a1, a1 * slope_h); a2 = fmaxf(a2, a2 * slope_h); a3 = fmaxf(a3, a3 * slope_h);
           if (!in_clip) { a0 = a1 = a2 = a3 = 0.f; }     // conv_b pads h with zeros outside the clip
           amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(a2), fabsf(a3))));
@@ -214,48 +224,73 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
     }
     if (!(amax <= 65504.f) && P.err) atomicCAS(P.err, 0, ERR_FP16_OVERFLOW);
   } else {
-    // ------------------------------------------------------------------ E2: accumulator 2 + bias_b + x -> x_new planes, activated plane
+    // ------------------------------------------------------------------ E2: accumulator 2 + bias_b + x -> x_new, activated plane
+    // The residual stream x of a fused stack is fp32 (F32_IN / out_f32: same 4 bytes per element as the hi/lo planes the
+    // un-fused layers exchange, but no hi/lo split and no half -> float conversions in this role: ~640 -> ~450 instructions per
+    // tile and warp, 2.62 -> 2.33 ms per pair).  The first pair of a stack still reads planes.  Measured alternatives: 16 warps
+    // of 16 columns (four per scheduler, half the dependent chain each) are SLOWER, 2.72 ms - the stores of a warp then cover
+    // 64-byte pieces of 256-byte rows, and ncu shows the kernel waiting on its global stores at 58 % DRAM utilisation.
     const int ew = warp - (2 + PAIR_E1_WARPS);
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // which 32-column chunk this warp takes (two warps share a lane quarter)
-    uint4* stg_h = reinterpret_cast<uint4*>(stg_base) + (size_t)ew * 256;     // 4 KB per warp: two 32 x 64-byte tiles
+    float4* stg_f = reinterpret_cast<float4*>(stg_base) + (size_t)ew * 256;   // 4 KB per warp
+    uint4* stg_h = reinterpret_cast<uint4*>(stg_f);                           // fp16 tiles alias it: two 32 x 64-byte tiles
     uint4* stg_l = stg_h + 128;
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
-    const int h_row = lane >> 2, h_c16 = lane & 3;          // row-major role: 8 rows x 64 B per instruction
+    const int h_row = lane >> 2, h_c16 = lane & 3;          // fp16 row-major role: 8 rows x 64 B per instruction
+    const int f_row = lane >> 3, f_c16 = lane & 7;          // fp32 row-major role: 4 rows x 128 B per instruction
     const int so_h0 = lane * 4, so_hx = (lane >> 1) & 3;
     const int sr_h0 = h_row * 4, sr_hx = h_c16;
+    const int so_f0 = lane * 8, so_fx = lane & 7;
+    const int sr_f0 = f_row * 8;
 #define PSO_H(i) (so_h0 + ((i) ^ so_hx))
 #define PSR_H(i) (32 * (i) + sr_h0 + (sr_hx ^ ((h_row >> 1) & 3)))
+#define PSO_F(i) (so_f0 + ((i) ^ so_fx))
+#define PSR_F(i) (32 * (i) + sr_f0 + (f_c16 ^ ((4 * (i) + f_row) & 7)))
     const float slope_out = P.slope_out;
-    const bool want_r = P.out_r_hi != nullptr;
+    const bool want_f = P.out_f32 != nullptr;
     const int wrow0 = q * 32;                  // first accumulator row of this warp
-    const int jrow = wrow0 + lane;             // this thread's accumulator row
     float amax = 0.f;
     bool ok = true;
+    // Residual of a tile in the row-major role, fetched ONE TILE AHEAD (it is consumed right after the accumulator read).
+    uint4 xr[8];                               // F32_IN: 8 x float4 (rows 4i + f_row); planes: [0,4) hi, [4,8) lo (rows 8i + h_row)
+    long base_next = 0;                        // element offset of this warp's first row and column chunk (next tile)
+    int m0_next = 0;
+    auto row_ok = [&](int m0, int jr) { return jr >= 1 && jr <= PAIR_ROWS && m0 + jr < P.L; };
+    auto load_resid = [&](int jj) {
+      const int tile = blockIdx.x + jj * gridDim.x;
+      const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
+      m0_next = (tile - img * P.tiles_per_img) * PAIR_ROWS - 1;
+      base_next = ((long)img * P.L + (m0_next + wrow0)) * C + half * 32;     // row -1 of a clip's first tile is never dereferenced
+      if (F32_IN) {
+        const float4* g = reinterpret_cast<const float4*>(P.resid_f32 + base_next + (long)f_row * C) + f_c16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xr[i] = make_uint4(0, 0, 0, 0);
+          if (row_ok(m0_next, wrow0 + 4 * i + f_row)) xr[i] = __ldg(reinterpret_cast<const uint4*>(g + i * C));   // 4 rows further = 4 C floats = C float4
+        }
+      } else {
+        const uint4* gh = reinterpret_cast<const uint4*>(P.resid_hi + base_next + (long)h_row * C) + h_c16;
+        const uint4* gl = reinterpret_cast<const uint4*>(P.resid_lo + base_next + (long)h_row * C) + h_c16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xr[i] = make_uint4(0, 0, 0, 0); xr[4 + i] = make_uint4(0, 0, 0, 0);
+          if (row_ok(m0_next, wrow0 + 8 * i + h_row)) {
+            xr[i] = __ldg(gh + i * C);                                      // 8 rows further = 8 C halves = C uint4
+            xr[4 + i] = __ldg(gl + i * C);
+          }
+        }
+      }
+    };
+    if (n_local > 0) load_resid(0);
     for (int j = 0; j < n_local && ok; ++j) {
       const int tile = blockIdx.x + j * gridDim.x;
       const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
-      const int m0 = (tile - img * P.tiles_per_img) * PAIR_ROWS - 1;
+      const int m0 = m0_next;
       const int b = j & 1;
       const uint32_t pj = (j >> 1) & 1;
-      const bool in_clip = (m0 + jrow) >= 0 && (m0 + jrow) < P.L;
-      // element offsets of this warp's first row (row -1 of the first tile is never dereferenced: guarded by jr >= 1)
-      const long in_base = ((long)img * P.L + (m0 + wrow0)) * C + half * 32;
+      const long in_base = base_next;
       const long out_base = ((long)img * P.out_img_rows + P.out_row0 + (m0 + wrow0)) * C + half * 32;
-      // residual x (hi + lo planes) of this tile: issued before the accumulator wait, so its latency hides behind P2 / E1
-      uint4 xh[4], xl[4];
-      bool valid[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = 8 * i + h_row, jr = wrow0 + rr, tt = m0 + jr;
-        valid[i] = jr >= 1 && jr <= PAIR_ROWS && tt < P.L;
-        xh[i] = make_uint4(0, 0, 0, 0); xl[i] = make_uint4(0, 0, 0, 0);
-        if (valid[i]) {
-          const long o = in_base + (long)rr * C;
-          xh[i] = __ldg(reinterpret_cast<const uint4*>(P.resid_hi + o) + h_c16);
-          xl[i] = __ldg(reinterpret_cast<const uint4*>(P.resid_lo + o) + h_c16);
-        }
-      }
       if (!mbar_wait(acc2_full + b, pj, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       tc_fence_after();
       float v[32];
@@ -270,55 +305,52 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
       }
       // coalesced row-major residual -> staging -> own row
       __syncwarp();
+      if (F32_IN) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        stg_h[PSR_H(i)] = xh[i];
-        stg_l[PSR_H(i)] = xl[i];
-      }
-      __syncwarp();
+        for (int i = 0; i < 8; ++i) stg_f[PSR_F(i)] = *reinterpret_cast<const float4*>(&xr[i]);
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 yh = stg_h[PSO_H(i)], yl = stg_l[PSO_H(i)];
-        const __half2* ph2 = reinterpret_cast<const __half2*>(&yh);
-        const __half2* pl2 = reinterpret_cast<const __half2*>(&yl);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 fh = __half22float2(ph2[k]), fl = __half22float2(pl2[k]);
-          v[8 * i + 2 * k] += fh.x + fl.x;
-          v[8 * i + 2 * k + 1] += fh.y + fl.y;
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = stg_f[PSO_F(i)];
+          v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
         }
-      }
-      if (want_r) {                           // raw hi/lo planes of x_new
-        uint32_t hi[16], lo[16];
+      } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-          const float2 f = __half22float2(hh);
-          const __half2 ll = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
-          hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
-          lo[i] = *reinterpret_cast<const uint32_t*>(&ll);
+        for (int i = 0; i < 4; ++i) {
+          stg_h[PSR_H(i)] = xr[i];
+          stg_l[PSR_H(i)] = xr[4 + i];
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          stg_h[PSO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-          stg_l[PSO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          const uint4 yh = stg_h[PSO_H(i)], yl = stg_l[PSO_H(i)];
+          const __half2* ph2 = reinterpret_cast<const __half2*>(&yh);
+          const __half2* pl2 = reinterpret_cast<const __half2*>(&yl);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 fh = __half22float2(ph2[k]), fl = __half22float2(pl2[k]);
+            v[8 * i + 2 * k] += fh.x + fl.x;
+            v[8 * i + 2 * k + 1] += fh.y + fl.y;
+          }
         }
+      }
+      if (j + 1 < n_local) load_resid(j + 1);   // in flight while this tile is packed and stored
+      if (want_f) {                             // x_new, fp32 stream of the stack
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (valid[i]) {
-            const long o = in_base + (long)(8 * i + h_row) * C;            // x_new planes have the clip's own row pitch
-            reinterpret_cast<uint4*>(P.out_r_hi + o)[h_c16] = stg_h[PSR_H(i)];
-            reinterpret_cast<uint4*>(P.out_r_lo + o)[h_c16] = stg_l[PSR_H(i)];
-          }
+        for (int i = 0; i < 8; ++i) stg_f[PSO_F(i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        __syncwarp();
+        float4* g = reinterpret_cast<float4*>(P.out_f32 + in_base + (long)f_row * C) + f_c16;    // the clip's own row pitch
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (row_ok(m0, wrow0 + 4 * i + f_row)) g[i * C] = stg_f[PSR_F(i)];
       }
       {                                         // activated plane for the next pair / stage
         uint32_t hi[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a0 = fmaxf(v[2 * i], v[2 * i] * slope_out), a1 = fmaxf(v[2 * i + 1], v[2 * i + 1] * slope_out);
-          if (in_clip && jrow >= 1 && jrow <= PAIR_ROWS) amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
+          amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));     // every row is finite (H border rows are zeroed)
           const __half2 hh = __floats2half2_rn(a0, a1);
           hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
         }
@@ -326,14 +358,17 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 4; ++i) stg_h[PSO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
         __syncwarp();
+        uint4* g = reinterpret_cast<uint4*>(P.out_a + out_base + (long)h_row * C) + h_c16;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (valid[i]) reinterpret_cast<uint4*>(P.out_a + out_base + (long)(8 * i + h_row) * C)[h_c16] = stg_h[PSR_H(i)];
+          if (row_ok(m0, wrow0 + 8 * i + h_row)) g[i * C] = stg_h[PSR_H(i)];
       }
     }
     if (!(amax <= 65504.f) && P.err) atomicCAS(P.err, 0, ERR_FP16_OVERFLOW);
 #undef PSO_H
 #undef PSR_H
+#undef PSO_F
+#undef PSR_F
   }
   tc_fence_before();
   __syncthreads();
@@ -345,16 +380,21 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
 
 size_t pair_tc_smem_bytes(int C, int /*stages*/) { return C == PAIR_C ? (size_t)PAIR_SMEM : 0; }
 
-cudaError_t launch_pair_tc(const PairParams& p, cudaStream_t stream) {
-  if (p.C != PAIR_C) return cudaErrorInvalidValue;
+template <bool F32_IN>
+static cudaError_t launch_pair_t(const PairParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<F32_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  pair_tc_kernel<<<p.grid, PAIR_THREADS, PAIR_SMEM, stream>>>(p);
+  pair_tc_kernel<F32_IN><<<p.grid, PAIR_THREADS, PAIR_SMEM, stream>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_pair_tc(const PairParams& p, cudaStream_t stream) {
+  if (p.C != PAIR_C) return cudaErrorInvalidValue;
+  return p.resid_f32 ? launch_pair_t<true>(p, stream) : launch_pair_t<false>(p, stream);
 }
 
 }  // namespace vf
