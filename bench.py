@@ -223,8 +223,10 @@ def stage_roofline(prof, stage_ms, peaks, clips, n_samples, frames, ssr=False):
 def dominant_kernel(prof, peaks):
     groups = {}
     for r in prof:
-        if r["bn"]:
-            g = groups.setdefault((r["bn"], r["bk"], r.get("terms", 0)), {"ms": 0.0, "flops": 0.0, "exec": 0.0, "bytes": 0.0, "n": 0, "ops": []})
+        pair = r["label"].endswith(".pair")        # pair_tc_kernel (fused residual pair) is its own kernel class
+        if r["bn"] or pair:
+            key = ("pair", 64, 1) if pair else (r["bn"], r["bk"], r.get("terms", 0))
+            g = groups.setdefault(key, {"ms": 0.0, "flops": 0.0, "exec": 0.0, "bytes": 0.0, "n": 0, "ops": []})
             g["ms"] += r["ms"]; g["flops"] += r["flops"]; g["exec"] += r.get("exec_flops", 0.0); g["bytes"] += r["bytes"]; g["n"] += 1; g["ops"].append(r)
     total_ms = sum(r["ms"] for r in prof)
 
@@ -238,28 +240,29 @@ def dominant_kernel(prof, peaks):
     bound = "hbm" if f_h > f_t else "tensor"
     # dram__bytes of the ncu --set full capture of ONE launch of this group (profiles/traffic.json, regenerated from
     # this build by tools/run_profile.sh + tools/summarize_profiles.py), beside the engine's figure for the SAME label
-    traffic = None
+    traffic, traffic_detail = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         for r in top["ops"]:
             if r["label"] in tj:
-                traffic = {"label": r["label"], "ncu_dram_bytes_per_launch": tj[r["label"]]["dram_bytes"],
-                           "algorithmic_bytes_this_launch": r["bytes"],
-                           "ratio": tj[r["label"]]["dram_bytes"] / r["bytes"] if r["bytes"] else None,
-                           "build": tj[r["label"]].get("build", "see profiles/")}
+                traffic = tj[r["label"]]["dram_bytes"]
+                traffic_detail = {"label": r["label"], "ncu_dram_bytes_per_launch": traffic, "algorithmic_bytes_this_launch": r["bytes"],
+                                  "ratio": traffic / r["bytes"] if r["bytes"] else None, "source": "profiles/traffic.json (ncu --set full, tools/run_profile.sh)"}
                 break
     labels = [r["label"] for r in top["ops"]]
+    kname = (f"pair_tc_kernel (tcgen05 fused residual pair, C = 64, hi-only; layers: {labels[0]} ... {labels[-1]})" if bn == "pair" else
+             f"gemm_tc_kernel<BN={bn},BK={bk},{'3-term' if terms == 3 else 'hi-only'}> (tcgen05 flat-shift conv GEMM; layers: {labels[0]} ... {labels[-1]})")
     return {
-        "kernel": f"gemm_tc_kernel<BN={bn},BK={bk},{'3-term' if terms == 3 else 'hi-only'}> (tcgen05 flat-shift conv GEMM; layers: {labels[0]} ... {labels[-1]})",
+        "kernel": kname,
         "bound": bound,
         "achieved": gb if bound == "hbm" else tf, "peak": peaks["hbm_gbs"] if bound == "hbm" else peaks["tflops"],
         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": f_h if bound == "hbm" else f_t,
         "peak_source": peaks["source"] + (" STREAM copy" if bound == "hbm" else " bf16 dense (== fp16 rate), sustained"),
-        "traffic": traffic, "launches": top["n"], "avg_launch_ms": top["ms"] / top["n"], "share_of_step": top["ms"] / total_ms,
+        "traffic": traffic, "traffic_detail": traffic_detail, "launches": top["n"], "avg_launch_ms": top["ms"] / top["n"], "share_of_step": top["ms"] / total_ms,
         "algorithmic_gflop_per_launch": top["flops"] / top["n"] / 1e9, "algorithmic_gb_per_launch": top["bytes"] / top["n"] / 1e9,
         "tensor_frac": f_t, "tensor_frac_executed": top["exec"] / (top["ms"] * 1e-3) / 1e12 / peaks["tflops"], "hbm_frac": f_h,
-        "all_kernels": {f"gemm<{k[0]},{k[1]},{'3t' if k[2] == 3 else '1t'}>": {"ms": v["ms"], "launches": v["n"], "tflops": rates(v)[0], "min_gbs": rates(v)[1],
+        "all_kernels": {("pair_tc<64>" if k[0] == "pair" else f"gemm<{k[0]},{k[1]},{'3t' if k[2] == 3 else '1t'}>"): {"ms": v["ms"], "launches": v["n"], "tflops": rates(v)[0], "min_gbs": rates(v)[1],
                                                                    "tensor_frac": rates(v)[2], "hbm_frac": rates(v)[3]}
                         for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
     }
@@ -284,6 +287,7 @@ def run_b200(args):
     import torch.distributed as tdist
 
     ssr = args.workload == "ssr"
+    t0 = time.perf_counter()
     rank, world, local = vdist.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
@@ -302,9 +306,8 @@ def run_b200(args):
         layout = [(k, s, int(torch.tensor(s).prod()) if s else 1) for k, s in sorted(items)]
     else:
         layout = vdist.layout_from_arch()
-    t0 = time.perf_counter()
     if world > 1:
-        tdist.barrier()
+        tdist.barrier()                      # NCCL communicator creation happens here, not in the weight broadcast
     torch.cuda.synchronize()
     t_init = time.perf_counter()
     state = vdist.broadcast_state(state0, layout, dev)

@@ -78,3 +78,62 @@ def test_arch_keys_match_reference_state_dict():
     assert list(own) == list(mine)          # same registration order
     assert sum(int(torch.tensor(s).prod()) if s else 1 for k, s in mine.items()
                if not k.endswith("num_batches_tracked") and "running" not in k) == 65152867
+
+
+def test_plain_mappings_work_as_hp_and_unet_small_is_accepted():
+    """`hp` is any mapping with the reference's keys (a plain dict here); `unet_small: true` selects the same network
+    (gsr_voicefixer.py:51-53, models/components/unet_small.py) and `unet` wins when both are set (:49)."""
+    from voicefixer_main_b200 import SSR_UNet, VoiceFixer
+    hp = {"task": {"gsr": {"gsr_model": {"voicefixer": {"unet": False, "unet_small": True, "bi_gru": False, "dnn": False}}}},
+          "data": {"sampling_rate": 44100},
+          "model": {"mel_freq_bins": 128, "window_size": 2048, "hop_size": 441, "pad_mode": "reflect", "window": "hann", "channels_in": 1}}
+    assert VoiceFixer(hp).analysis_module_name == "unet_small"
+    hp["task"]["gsr"]["gsr_model"]["voicefixer"]["unet"] = True
+    assert VoiceFixer(hp).analysis_module_name == "unet"
+    s = SSR_UNet(hp)
+    assert s.generator is not None and s.downsample_ratio == 64
+
+
+def test_checkpoint_loading_is_explicit_about_the_vocoder(tmp_path):
+    """a reference Lightning checkpoint cannot supply the pip package's vocoder in loadable form; the mirror says
+    so instead of claiming drop-in loading, takes it as `vocoder_state`, and refuses strict=False."""
+    from voicefixer_main_b200 import VoiceFixer
+    from voicefixer_main_b200.model import Engine
+    from voicefixer_main_b200.weights import make_unet_state, make_vocoder_state
+    unet, voc = make_unet_state(1), make_vocoder_state(seed=2)
+    m = VoiceFixer()
+    with pytest.raises(NotImplementedError):
+        m.load_state_dict(unet, strict=False)
+    ck = tmp_path / "ckpt.pt"
+    torch.save({"state_dict": unet}, ck)
+    m.load_from_checkpoint(str(ck), vocoder_state={k[len("vocoder."):]: v for k, v in voc.items()})   # bare arch.vocoder_keys names
+    assert all(k in m.state_dict() for k in voc)
+    # without the vocoder tensors the engine-side loader names what is missing and where it comes from
+    eng = Engine.__new__(Engine)
+    eng.voc_cfg = m.voc_cfg
+    with pytest.raises(KeyError, match="vocoder"):
+        Engine.load_state(eng, unet)
+
+
+def test_resampler_filter_design_matches_scipy_firwin():
+    """edges.design_filter restates scipy.signal.resample_poly's default FIR; the kernel's index formula
+    out[m] = sum_i h[m*down - i*up + half] x[i] is resample_poly's (zero-phase upfirdn with its pre-padding folded in)."""
+    import numpy as np
+    from scipy.signal import firwin, resample_poly
+    from voicefixer_main_b200.edges import design_filter
+    rng = np.random.default_rng(0)
+    for up, down in ((147, 160), (441, 160), (441, 80), (2, 1), (147, 320)):
+        mr = max(up, down)
+        half = 10 * mr
+        ref = firwin(2 * half + 1, 1.0 / mr, window=("kaiser", 5.0)) * up
+        h = design_filter(up, down)
+        assert h.dtype == np.float32 and h.shape == ref.shape
+        assert float(np.abs(h - ref).max()) < 1e-6 * float(np.abs(ref).max())
+        x = rng.standard_normal(3001)
+        y = resample_poly(x, up, down)
+        n_out = -(-len(x) * up // down)
+        assert len(y) == n_out
+        for m in range(0, n_out, max(1, n_out // 40)):
+            c = m * down
+            i = np.arange(max(0, -(-(c - half) // up)), min(len(x) - 1, (c + half) // up) + 1)
+            assert abs(float(np.sum(ref[c - i * up + half] * x[i])) - y[m]) < 1e-9

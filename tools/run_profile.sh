@@ -16,7 +16,7 @@ G=$(python - <<'PY'
 import json
 ops=json.load(open('gpurun_out/op_profile.json'))['ops']
 g=[o['label'] for o in ops if o['bn']]
-want=['enc1.b2.conv1','enc3.b2.conv1','voc.res0.1.a','voc.res1.1.b','voc.res2.1.a','voc.res2.1.b','voc.res3.1.a','voc.res3.1.b']
+want=['enc1.b2.conv1','enc3.b2.conv1','voc.res0.1.a','voc.res1.1.b','voc.res2.1.a','voc.res2.1.b']
 print(len(g), ' '.join(f"{w.replace('.','_')}:{g.index(w)}" for w in want if w in g))
 PY
 )
@@ -30,7 +30,8 @@ for spec in $SPECS; do
   # gpurun copies back at most 64 MiB: keep the raw / source pages as CSV, and the binary report of two kernels only
   ncu -i gpurun_out/prof_$name.ncu-rep --page raw --csv > gpurun_out/prof_${name}_raw.csv 2>/dev/null
   ncu -i gpurun_out/prof_$name.ncu-rep --page source --csv 2>/dev/null | cut -c1-400 > gpurun_out/prof_${name}_source.csv
-  case $name in voc_res3_1_b|enc1_b2_conv1) ;; *) rm -f gpurun_out/prof_$name.ncu-rep ;; esac
+  case $name in enc1_b2_conv1) ;; *) rm -f gpurun_out/prof_$name.ncu-rep ;; esac
 done
+bash tools/profile_pair.sh
 du -sh gpurun_out
 ls gpurun_out/
