@@ -562,6 +562,18 @@ struct Builder {
     if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(A: C=%d rows=%d img_rows=%d n=%d box=%d) -> %d", C, rows, img_rows, n_img, box_c, (int)r);
     return VF_OK;
   }
+  // generic [C, rows, image] map with SWIZZLE_128B (inner box = 128 bytes): TMA loads / stores of the fused pair kernel
+  int make_map3_any(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int esize, int C, int rows, size_t img_rows, int n_img,
+                    int box_c, int box_rows) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_img};
+    cuuint64_t strides[2] = {(cuuint64_t)C * esize, (cuuint64_t)img_rows * C * esize};
+    cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = ctx->encode(m, dt, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(pair: C=%d rows=%d box=%dx%d esize=%d) -> %d", C, rows, box_c, box_rows, esize, (int)r);
+    return VF_OK;
+  }
   // 3-term operands: hi and lo planes in ONE box ([C, rows, image, plane] / [K, N, plane]) - half the TMA issues
   int make_map4(CUtensorMap* m, const __half* base, int C, int rows, int img_rows, int n_img, size_t plane_stride, int box_c, bool sw128, int box_rows) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_img, 2};
@@ -1137,10 +1149,20 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         if (mrc) return mrc;
         pp.bias_a = ctx->voc_res_a[s][i].bias;
         pp.bias_b = ctx->voc_res_b[s][i].bias;
-        if (i == 0) { pp.resid_hi = xr[0].p.hi; pp.resid_lo = xr[0].p.lo; }      // written by the transposed conv above
-        else pp.resid_f32 = xf[curx];
-        if (!last) pp.out_f32 = xf[1 - curx];
-        pp.out_a = dst.p.hi;
+        const int orow0 = (last && last_stage) ? 3 : 0;
+        if (i == 0) {        // the stack's input: hi / lo planes written by the transposed conv above
+          mrc = b.make_map3_any(&pp.xin_map[0], xr[0].p.hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, (int)L, (size_t)L, B, 64, 126);
+          if (!mrc) mrc = b.make_map3_any(&pp.xin_map[1], xr[0].p.lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, (int)L, (size_t)L, B, 64, 126);
+        } else {
+          pp.in_f32 = 1;
+          mrc = b.make_map3_any(&pp.xin_map[0], xf[curx], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, (int)L, (size_t)L, B, 32, 126);
+        }
+        if (!mrc && !last) {
+          pp.out_f32 = 1;
+          mrc = b.make_map3_any(&pp.xo_map, xf[1 - curx], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, (int)L, (size_t)L, B, 32, 126);
+        }
+        if (!mrc) mrc = b.make_map3_any(&pp.ao_map, dst.p.hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, orow0 + (int)L, (size_t)dst.img_rows, B, 64, 126);
+        if (mrc) return mrc;
         pp.L = (int)L; pp.n_img = B; pp.C = cout; pp.dil = dil;
         pp.out_img_rows = dst.img_rows;
         pp.out_row0 = (last && last_stage) ? 3 : 0;

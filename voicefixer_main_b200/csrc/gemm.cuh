@@ -114,17 +114,18 @@ struct GemmTcParams {
   GemmProblem prob;
 };
 
-// Fused residual pair of the vocoder stacks (pair_tc.cu, experimental / opt-in): x_new = x + conv_b(lrelu(conv_a(xa) + bias_a)) + bias_b
+// Fused residual pair of the C = 64 vocoder stacks (pair_tc.cu): x_new = x + conv_b(lrelu(conv_a(xa) + bias_a)) + bias_b
 struct PairParams {
   CUtensorMap a_map;             // activated input plane lrelu(x), hi: [C, L, clips], box 64 x 128 x 1, SWIZZLE_128B
   CUtensorMap wa_map, wb_map;    // packed K-major hi weights [K >= 3C, C], box 64 x C
+  CUtensorMap xin_map[2];        // residual x.  in_f32: [0] = the stack's fp32 stream [C, L, clips] (box 32 x 126 x 1, used for
+                                 // both channel halves); else [0] / [1] = its hi / lo fp16 planes (box 64 x 126 x 1), written
+                                 // by the up-sampling GEMM in front of the stack
+  CUtensorMap xo_map;            // x_new, fp32 stream (box 32 x 126 x 1); unused when out_f32 == 0 (last pair of a stage)
+  CUtensorMap ao_map;            // lrelu(x_new, slope_out), hi plane [C, out_row0 + L, clips] (box 64 x 126 x 1)
   const float* bias_a;
   const float* bias_b;
-  const __half* resid_hi;        // x as hi/lo planes [clips, L, C] (first pair of a stack: written by the up-sampling GEMM) ...
-  const __half* resid_lo;
-  const float* resid_f32;        // ... or as the stack's fp32 stream [clips, L, C] (non-null selects it)
-  float* out_f32;                // x_new, fp32 stream (null for the last pair of a stage)
-  __half* out_a;                 // lrelu(x_new, slope_out), hi plane [clips, out_img_rows, C], first row out_row0
+  int in_f32, out_f32;
   int L, n_img, C, dil, out_img_rows, out_row0, tiles_per_img, stages, grid;
   uint32_t magic_t;              // gemm_tc_magic(tiles_per_img, ...)
   float slope_h, slope_out;

@@ -2,7 +2,8 @@
 //     x_new = x + conv_b(lrelu(conv_a(lrelu(x)) + bias_a)) + bias_b          (oracle: vocoder_generator, the `res.s.i` pair)
 // conv_a: k = 3, dilation d, zero padding;  conv_b: k = 3, dilation 1, zero padding.  hi-only fp16 operands, fp32
 // accumulation (the vocoder's 1-term mode).  What two separate GEMM launches move through HBM in between - the activated
-// intermediate h, written by "a" and read back by "b" (4 of 16 bytes per element) - stays in shared memory.
+// intermediate h, written by "a" and read back by "b" (4 of 16 bytes per element) - stays in shared memory, and the
+// residual stream of a fused stack is fp32 (same 4 bytes per element as the hi/lo planes, no split arithmetic).
 //
 //   tile = 126 output rows t0 .. t0+125 of one clip, m0 = t0 - 1.
 //   P1 (conv_a)   A = lrelu(x) rows m0 + (tap-1) d + [0,128) by TMA (out-of-range rows zero filled), accumulator 1 = h rows
@@ -12,20 +13,25 @@
 //                 buffer row k + 1: the three taps of conv_b are row-shifted views, start rows 0/1/2 - legal with
 //                 base_offset = 0, tools/probe_desc_shift.cu)
 //   P2 (conv_b)   A = H views, accumulator 2 = output rows m0 .. m0+127, of which 1..126 are valid
-//   E2            + bias_b + x (hi + lo planes), raw hi/lo planes of x_new and the activated hi plane for the next pair
+//   E2            + bias_b + x, x_new (fp32) and the activated fp16 plane of the next pair
 //
-// Round 1's version ran E1 and E2 on the same warps, one tile at a time: every tile paid the whole TMA -> P1 -> E1 -> P2 ->
-// E2 latency chain and the kernel measured 30 % SLOWER than the two launches it replaces (3.2 vs 2.5 ms per pair).  Here each
-// step has its own warps and every inter-step buffer is double buffered, so the steps of consecutive tiles overlap and the
-// throughput is set by the slowest role (E2, the HBM traffic) instead of the sum:
-//   warp 0       TMA producer: one 3-tap A stage (48 KB) per tile, two stages; both weight matrices (2 x 3 x 8 KB) are
-//                loaded once and stay resident
-//   warp 1       MMA issuer, software pipelined P1(j+1) before P2(j); 12 MMAs per barrier round trip, descriptors
-//                precomputed per stage (the issue thread's per-chunk instruction count bounds narrow tiles)
-//   warps 2-5    E1: accumulator 1 -> H (two H buffers)
-//   warps 6-13   E2: residual (fp32 stream of the stack; hi/lo planes for its first pair) prefetched one tile ahead,
-//                accumulator 2 -> fp32 x_new + the activated fp16 plane of the next pair
-// Every wait is bounded (ptx.cuh).
+// History of this kernel, all measured on the B200 (B = 32 x 10 s, ms per pair; the two launches it replaces take 2.49):
+//   r1   one warp group for E1 and E2, one tile at a time                                            3.23   (serial latency chain)
+//   r2a  one warp group per step, double-buffered H / accumulators, resident weights                 2.60
+//   r2b  + fp32 stream of the stack instead of hi/lo planes (E2: 640 -> 450 instructions per tile)   2.33
+//   r2c  16 E2 warps of 16 columns                                                                    2.72   (more, smaller LSU requests)
+//   ncu on r2b/r2c: l1tex__data_pipe_lsu_wavefronts 84 % of peak - the LSU data pipe, fed by the LDG/STG of E2 and the
+//   STS/LDS of its row-per-thread <-> row-major staging transposes, is the limiter (DRAM at 58-65 %).  Hence this version:
+//   r2d  the residual tile arrives by TMA (SWIZZLE_128B, read conflict-free by the row's own thread), x_new is written
+//        back IN PLACE and leaves by TMA store, as does the activated tile: no LDG / STG, no staging transposes.
+//
+// Warp roles (every wait is bounded, ptx.cuh):
+//   warp 0       TMA producer: ring of four A tap slots (16 KB each), two residual stages (2 x 16 KB each); both weight
+//                matrices (2 x 3 x 8 KB) are loaded once and stay resident
+//   warp 1       MMA issuer, software pipelined P1(j+1) before P2(j); 12 MMAs per phase, descriptors precomputed
+//   warps 2-5    E1: accumulator 1 -> H
+//   warps 6-13   E2: accumulator 2 + residual tile -> x_new in place + activated tile
+//   warp 14      TMA stores of x_new / the activated tile, then hands the stage back to the producer
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -35,13 +41,24 @@ namespace {
 constexpr int PAIR_C = 64;
 constexpr int PAIR_ROWS = 126;                 // valid output rows per tile
 constexpr int PAIR_A_TAP = 128 * 128;          // one A box: 128 rows x 64 channels fp16
-constexpr int PAIR_A_STAGE = 3 * PAIR_A_TAP;   // the three dilated taps of one tile
 constexpr int PAIR_W_TAP = PAIR_C * 128;       // one weight tile: 64 output channels x 64 input channels fp16
 constexpr int PAIR_H_BUF = 136 * 128;          // 130 rows used, rounded up to whole 1024-byte swizzle atoms
+constexpr int PAIR_X_TILE = 128 * 128;         // residual / output half tile: 126 rows x 128 B (32 fp32 or 64 fp16 channels)
+constexpr int PAIR_X_STAGE = 2 * PAIR_X_TILE;
 constexpr int PAIR_E1_WARPS = 4, PAIR_E2_WARPS = 8;
 constexpr int PAIR_E1_THREADS = 32 * PAIR_E1_WARPS, PAIR_E2_THREADS = 32 * PAIR_E2_WARPS;
-constexpr int PAIR_THREADS = 64 + PAIR_E1_THREADS + PAIR_E2_THREADS;
-constexpr int PAIR_SMEM = 2 * PAIR_A_STAGE + 6 * PAIR_W_TAP + 2 * PAIR_H_BUF + PAIR_E2_WARPS * 4096 + 256 + 2 * PAIR_C * 4 + 1024;
+constexpr int PAIR_THREADS = 64 + PAIR_E1_THREADS + PAIR_E2_THREADS + 32;
+constexpr int PAIR_SMEM = 4 * PAIR_A_TAP + 6 * PAIR_W_TAP + PAIR_H_BUF + 2 * PAIR_X_STAGE + PAIR_X_TILE + 512 + 2 * PAIR_C * 4 + 1024;
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void e2_bar_sync() { asm volatile("bar.sync 2, %0;" ::"r"(PAIR_E2_THREADS) : "memory"); }
 }  // namespace
 
 template <bool F32_IN>
@@ -52,21 +69,26 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_base = smem;                                   // [2][3][128 x 128 B]
-  uint8_t* w_base = a_base + 2 * PAIR_A_STAGE;              // [Wa tap 0..2][Wb tap 0..2], 8 KB each
-  uint8_t* h_base = w_base + 6 * PAIR_W_TAP;                // [2][136 x 128 B]
-  uint8_t* stg_base = h_base + 2 * PAIR_H_BUF;              // E2: 8 x 4 KB staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + PAIR_E2_WARPS * 4096);
+  uint8_t* a_base = smem;                                   // [4] tap slots of 128 x 128 B
+  uint8_t* w_base = a_base + 4 * PAIR_A_TAP;                // [Wa tap 0..2][Wb tap 0..2], 8 KB each
+  uint8_t* h_base = w_base + 6 * PAIR_W_TAP;                // 136 x 128 B
+  uint8_t* x_base = h_base + PAIR_H_BUF;                    // [2 stages][2 half tiles] (fp32: channel halves; planes: hi, lo)
+  uint8_t* act_base = x_base + 2 * PAIR_X_STAGE;            // activated output tile, 126 x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(act_base + PAIR_X_TILE);
   uint64_t* w_full = bars;            // [1]
-  uint64_t* a_full = bars + 1;        // [2]
-  uint64_t* a_empty = bars + 3;       // [2]
-  uint64_t* acc1_full = bars + 5;     // [2]
-  uint64_t* acc1_empty = bars + 7;    // [2]
-  uint64_t* h_ready = bars + 9;       // [2]
-  uint64_t* h_free = bars + 11;       // [2]
-  uint64_t* acc2_full = bars + 13;    // [2]
-  uint64_t* acc2_empty = bars + 15;   // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* a_full = bars + 1;        // [4]
+  uint64_t* a_empty = bars + 5;       // [4]
+  uint64_t* acc1_full = bars + 9;     // [2]
+  uint64_t* acc1_empty = bars + 11;   // [2]
+  uint64_t* h_ready = bars + 13;      // [1]
+  uint64_t* h_free = bars + 14;       // [1]
+  uint64_t* acc2_full = bars + 15;    // [2]
+  uint64_t* acc2_empty = bars + 17;   // [2]
+  uint64_t* x_full = bars + 19;       // [2] residual stage loaded
+  uint64_t* x_empty = bars + 21;      // [2] ... stored / released (store warp)
+  uint64_t* out_ready = bars + 23;    // [2] E2 has finished the stage and the activated tile
+  uint64_t* act_free = bars + 25;     // [1] the activated tile has been read by its TMA store
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
   float* s_bias_a = reinterpret_cast<float*>(bars + 32);   // [C] (16-byte aligned)
   float* s_bias_b = s_bias_a + C;                          // [C]
 
@@ -74,19 +96,25 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
   const int total_tiles = P.n_img * P.tiles_per_img;
   const int n_local = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   constexpr int TMEM_COLS = 4 * C;               // accumulator 1 x 2 at columns 0 / C, accumulator 2 x 2 at 2C / 3C
+  const bool want_f = P.out_f32 != 0;
 
   if (warp == 0 && lane == 0) {
     mbar_init(w_full, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1);
       mbar_init(acc1_full + i, 1); mbar_init(acc1_empty + i, PAIR_E1_THREADS);
-      mbar_init(h_ready + i, PAIR_E1_THREADS); mbar_init(h_free + i, 1);
       mbar_init(acc2_full + i, 1); mbar_init(acc2_empty + i, PAIR_E2_THREADS);
+      mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1);
+      mbar_init(out_ready + i, PAIR_E2_THREADS);
     }
+    mbar_init(h_ready, PAIR_E1_THREADS); mbar_init(h_free, 1);
+    mbar_init(act_free, 1);
     fence_mbar_init();
     tma_prefetch_desc(&P.a_map);
     tma_prefetch_desc(&P.wa_map);
     tma_prefetch_desc(&P.wb_map);
+    tma_prefetch_desc(&P.xin_map[0]);
+    tma_prefetch_desc(&P.ao_map);
   }
   if (warp == 1) tmem_alloc_dyn(tmem_holder, TMEM_COLS);
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -107,18 +135,31 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
         tma_load_2d(w_base + (3 + t) * PAIR_W_TAP, &P.wb_map, w_full, t * C, 0);
       }
       bool ok = true;
+      uint32_t n = 0;                 // A tap counter: slot n & 3, phase (n >> 2) & 1
       for (int j = 0; j < n_local && ok; ++j) {
         const int tile = blockIdx.x + j * gridDim.x;
         const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
-        const int m0 = (tile - img * P.tiles_per_img) * PAIR_ROWS - 1;
-        const int b = j & 1;
-        const uint32_t pj = (j >> 1) & 1;
-        if (!mbar_wait(a_empty + b, pj ^ 1u, P.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
-        uint8_t* st = a_base + b * PAIR_A_STAGE;
-        mbar_expect_tx(a_full + b, PAIR_A_STAGE);
-        tma_load_3d(st, &P.a_map, a_full + b, 0, m0 - P.dil, img);
-        tma_load_3d(st + PAIR_A_TAP, &P.a_map, a_full + b, 0, m0, img);
-        tma_load_3d(st + 2 * PAIR_A_TAP, &P.a_map, a_full + b, 0, m0 + P.dil, img);
+        const int t0 = (tile - img * P.tiles_per_img) * PAIR_ROWS;
+        const int m0 = t0 - 1;
+        for (int t = 0; t < 3 && ok; ++t, ++n) {
+          const uint32_t sl = n & 3u;
+          if (!mbar_wait(a_empty + sl, ((n >> 2) & 1u) ^ 1u, P.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+          mbar_expect_tx(a_full + sl, PAIR_A_TAP);
+          tma_load_3d(a_base + sl * PAIR_A_TAP, &P.a_map, a_full + sl, 0, m0 + (t - 1) * P.dil, img);
+        }
+        if (!ok) break;
+        // residual tile of rows t0 .. t0+125 (rows past the clip are zero filled; they are clipped again on the way out)
+        const int s = j & 1;
+        if (!mbar_wait(x_empty + s, ((j >> 1) & 1) ^ 1, P.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+        uint8_t* xs = x_base + s * PAIR_X_STAGE;
+        mbar_expect_tx(x_full + s, 2 * PAIR_ROWS * 128);
+        if (F32_IN) {
+          tma_load_3d(xs, &P.xin_map[0], x_full + s, 0, t0, img);                    // channels 0..31
+          tma_load_3d(xs + PAIR_X_TILE, &P.xin_map[0], x_full + s, 32, t0, img);     // channels 32..63
+        } else {
+          tma_load_3d(xs, &P.xin_map[0], x_full + s, 0, t0, img);                    // hi plane
+          tma_load_3d(xs + PAIR_X_TILE, &P.xin_map[1], x_full + s, 0, t0, img);      // lo plane
+        }
       }
     }
     __syncwarp();
@@ -127,32 +168,32 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
     if (elect_one()) {
       const uint32_t da0 = make_smem_desc_lo(smem_u32(a_base));
       const uint32_t dw0 = make_smem_desc_lo(smem_u32(w_base));
-      const uint32_t dh0 = make_smem_desc_lo(smem_u32(h_base));
+      const uint32_t dh = make_smem_desc_lo(smem_u32(h_base));
       bool ok = mbar_wait(w_full, 0, P.err, ERR_PIPE_MMA);
+      uint32_t n = 0;
       for (int j = 0; j <= n_local && ok; ++j) {
         if (j < n_local) {          // ---- P1(j): conv_a into accumulator 1[b]
           const int b = j & 1;
-          const uint32_t pj = (j >> 1) & 1;
-          if (!mbar_wait(acc1_empty + b, pj ^ 1u, P.err, ERR_PIPE_MMA)) { ok = false; break; }
-          if (!mbar_wait(a_full + b, pj, P.err, ERR_PIPE_MMA)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t da = da0 + (uint32_t)(b * (PAIR_A_STAGE >> 4));
+          if (!mbar_wait(acc1_empty + b, ((j >> 1) & 1) ^ 1, P.err, ERR_PIPE_MMA)) { ok = false; break; }
           const uint32_t d = tmem_base + b * C;
+          for (int t = 0; t < 3 && ok; ++t, ++n) {
+            const uint32_t sl = n & 3u;
+            if (!mbar_wait(a_full + sl, (n >> 2) & 1u, P.err, ERR_PIPE_MMA)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t da = da0 + sl * (PAIR_A_TAP >> 4);
+            const uint32_t dw = dw0 + t * (PAIR_W_TAP >> 4);
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_lo(d, da + t * (PAIR_A_TAP >> 4) + 2 * k, dw0 + t * (PAIR_W_TAP >> 4) + 2 * k, DHI, IDESC, (t | k) ? 1u : 0u);
-          umma_commit(a_empty + b);
+            for (int k = 0; k < 4; ++k) umma_f16_lo(d, da + 2 * k, dw + 2 * k, DHI, IDESC, (t | k) ? 1u : 0u);
+            umma_commit(a_empty + sl);
+          }
+          if (!ok) break;
           umma_commit(acc1_full + b);
         }
-        if (j >= 1) {               // ---- P2(j-1): conv_b on H[b] into accumulator 2[b]
+        if (j >= 1) {               // ---- P2(j-1): conv_b on H into accumulator 2[b]
           const int i = j - 1, b = i & 1;
-          const uint32_t pi = (i >> 1) & 1;
-          if (!mbar_wait(h_ready + b, pi, P.err, ERR_PIPE_MMA)) { ok = false; break; }
-          if (!mbar_wait(acc2_empty + b, pi ^ 1u, P.err, ERR_PIPE_MMA)) { ok = false; break; }
+          if (!mbar_wait(h_ready, i & 1, P.err, ERR_PIPE_MMA)) { ok = false; break; }
+          if (!mbar_wait(acc2_empty + b, ((i >> 1) & 1) ^ 1, P.err, ERR_PIPE_MMA)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t dh = dh0 + (uint32_t)(b * (PAIR_H_BUF >> 4));
           const uint32_t d = tmem_base + 2 * C + b * C;
 #pragma unroll
           for (int t = 0; t < 3; ++t)
@@ -160,7 +201,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
             for (int k = 0; k < 4; ++k)      // view of tap t starts at buffer row t
               umma_f16_lo(d, dh + t * (128 >> 4) + 2 * k, dw0 + (3 + t) * (PAIR_W_TAP >> 4) + 2 * k, DHI, IDESC, (t | k) ? 1u : 0u);
           umma_commit(acc2_full + b);
-          umma_commit(h_free + b);
+          umma_commit(h_free);
         }
       }
     }
@@ -174,25 +215,23 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
     const float slope_h = P.slope_h;
     float amax = 0.f;
     bool ok = true;
-    // buffer rows 0 and 129 of both H buffers are read by the first / last tap of accumulator rows 0 and 127 (never stored,
-    // but they must stay finite for the overflow guard): zero them once, E1 only ever writes rows 1..128
-    if (warp == 2 && lane < 16) {
-      uint8_t* hb = h_base + (size_t)(lane >> 3) * PAIR_H_BUF;
-      *reinterpret_cast<uint4*>(hb + (lane & 7) * 16) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(hb + 129 * 128 + (lane & 7) * 16) = make_uint4(0, 0, 0, 0);
+    // buffer rows 0 and 129 are read by the first / last tap of accumulator rows 0 and 127 (never stored, but they must
+    // stay finite for the overflow guard): zero them once, E1 only ever writes rows 1..128
+    if (warp == 2 && lane < 8) {
+      *reinterpret_cast<uint4*>(h_base + lane * 16) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(h_base + 129 * 128 + lane * 16) = make_uint4(0, 0, 0, 0);
     }
+    uint8_t* rowp = h_base + (size_t)brow * 128;
     for (int j = 0; j < n_local && ok; ++j) {
       const int tile = blockIdx.x + j * gridDim.x;
       const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
       const int m0 = (tile - img * P.tiles_per_img) * PAIR_ROWS - 1;
       const int b = j & 1;
-      const uint32_t pj = (j >> 1) & 1;
       const int t = m0 + jrow;
       const bool in_clip = t >= 0 && t < P.L;
-      if (!mbar_wait(acc1_full + b, pj, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+      if (!mbar_wait(acc1_full + b, (j >> 1) & 1, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       tc_fence_after();
-      if (!mbar_wait(h_free + b, pj ^ 1u, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }   // P2(j-2) has read H[b]
-      uint8_t* rowp = h_base + (size_t)b * PAIR_H_BUF + (size_t)brow * 128;
+      if (!mbar_wait(h_free, (j & 1) ^ 1, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }      // P2(j-1) has read H
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {              // two passes of 32 columns
         float v[32];
@@ -220,77 +259,28 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
           *reinterpret_cast<uint4*>(rowp + (((c * 4 + i) ^ (brow & 7)) << 4)) = make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
       }
       fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's async proxy
-      mbar_arrive(h_ready + b);
+      mbar_arrive(h_ready);
     }
     if (!(amax <= 65504.f) && P.err) atomicCAS(P.err, 0, ERR_FP16_OVERFLOW);
-  } else {
-    // ------------------------------------------------------------------ E2: accumulator 2 + bias_b + x -> x_new, activated plane
-    // The residual stream x of a fused stack is fp32 (F32_IN / out_f32: same 4 bytes per element as the hi/lo planes the
-    // un-fused layers exchange, but no hi/lo split and no half -> float conversions in this role: ~640 -> ~450 instructions per
-    // tile and warp, 2.62 -> 2.33 ms per pair).  The first pair of a stack still reads planes.  Measured alternatives: 16 warps
-    // of 16 columns (four per scheduler, half the dependent chain each) are SLOWER, 2.72 ms - the stores of a warp then cover
-    // 64-byte pieces of 256-byte rows, and ncu shows the kernel waiting on its global stores at 58 % DRAM utilisation.
+  } else if (warp < 2 + PAIR_E1_WARPS + PAIR_E2_WARPS) {
+    // ------------------------------------------------------------------ E2: accumulator 2 + bias_b + x -> x_new (in place), activated tile
     const int ew = warp - (2 + PAIR_E1_WARPS);
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // which 32-column chunk this warp takes (two warps share a lane quarter)
-    float4* stg_f = reinterpret_cast<float4*>(stg_base) + (size_t)ew * 256;   // 4 KB per warp
-    uint4* stg_h = reinterpret_cast<uint4*>(stg_f);                           // fp16 tiles alias it: two 32 x 64-byte tiles
-    uint4* stg_l = stg_h + 128;
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
-    const int h_row = lane >> 2, h_c16 = lane & 3;          // fp16 row-major role: 8 rows x 64 B per instruction
-    const int f_row = lane >> 3, f_c16 = lane & 7;          // fp32 row-major role: 4 rows x 128 B per instruction
-    const int so_h0 = lane * 4, so_hx = (lane >> 1) & 3;
-    const int sr_h0 = h_row * 4, sr_hx = h_c16;
-    const int so_f0 = lane * 8, so_fx = lane & 7;
-    const int sr_f0 = f_row * 8;
-#define PSO_H(i) (so_h0 + ((i) ^ so_hx))
-#define PSR_H(i) (32 * (i) + sr_h0 + (sr_hx ^ ((h_row >> 1) & 3)))
-#define PSO_F(i) (so_f0 + ((i) ^ so_fx))
-#define PSR_F(i) (32 * (i) + sr_f0 + (f_c16 ^ ((4 * (i) + f_row) & 7)))
+    const int jrow = q * 32 + lane;            // this thread's accumulator row
+    const bool row_valid = jrow >= 1 && jrow <= PAIR_ROWS;      // accumulator rows 0 and 127 are halo rows
+    const int xrow = row_valid ? jrow - 1 : 0; // its row in the residual / output tiles
+    const uint32_t sw = (uint32_t)(xrow & 7);  // SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
     const float slope_out = P.slope_out;
-    const bool want_f = P.out_f32 != nullptr;
-    const int wrow0 = q * 32;                  // first accumulator row of this warp
     float amax = 0.f;
     bool ok = true;
-    // Residual of a tile in the row-major role, fetched ONE TILE AHEAD (it is consumed right after the accumulator read).
-    uint4 xr[8];                               // F32_IN: 8 x float4 (rows 4i + f_row); planes: [0,4) hi, [4,8) lo (rows 8i + h_row)
-    long base_next = 0;                        // element offset of this warp's first row and column chunk (next tile)
-    int m0_next = 0;
-    auto row_ok = [&](int m0, int jr) { return jr >= 1 && jr <= PAIR_ROWS && m0 + jr < P.L; };
-    auto load_resid = [&](int jj) {
-      const int tile = blockIdx.x + jj * gridDim.x;
-      const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
-      m0_next = (tile - img * P.tiles_per_img) * PAIR_ROWS - 1;
-      base_next = ((long)img * P.L + (m0_next + wrow0)) * C + half * 32;     // row -1 of a clip's first tile is never dereferenced
-      if (F32_IN) {
-        const float4* g = reinterpret_cast<const float4*>(P.resid_f32 + base_next + (long)f_row * C) + f_c16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xr[i] = make_uint4(0, 0, 0, 0);
-          if (row_ok(m0_next, wrow0 + 4 * i + f_row)) xr[i] = __ldg(reinterpret_cast<const uint4*>(g + i * C));   // 4 rows further = 4 C floats = C float4
-        }
-      } else {
-        const uint4* gh = reinterpret_cast<const uint4*>(P.resid_hi + base_next + (long)h_row * C) + h_c16;
-        const uint4* gl = reinterpret_cast<const uint4*>(P.resid_lo + base_next + (long)h_row * C) + h_c16;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          xr[i] = make_uint4(0, 0, 0, 0); xr[4 + i] = make_uint4(0, 0, 0, 0);
-          if (row_ok(m0_next, wrow0 + 8 * i + h_row)) {
-            xr[i] = __ldg(gh + i * C);                                      // 8 rows further = 8 C halves = C uint4
-            xr[4 + i] = __ldg(gl + i * C);
-          }
-        }
-      }
-    };
-    if (n_local > 0) load_resid(0);
+    uint8_t* act_row = act_base + (size_t)xrow * 128;
     for (int j = 0; j < n_local && ok; ++j) {
-      const int tile = blockIdx.x + j * gridDim.x;
-      const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
-      const int m0 = m0_next;
-      const int b = j & 1;
+      const int b = j & 1, s = j & 1;
       const uint32_t pj = (j >> 1) & 1;
-      const long in_base = base_next;
-      const long out_base = ((long)img * P.out_img_rows + P.out_row0 + (m0 + wrow0)) * C + half * 32;
+      uint8_t* xs = x_base + s * PAIR_X_STAGE;
+      if (!mbar_wait(x_full + s, pj, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       if (!mbar_wait(acc2_full + b, pj, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       tc_fence_after();
       float v[32];
@@ -303,72 +293,83 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
         const float4 b4 = bp[i];
         v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
       }
-      // coalesced row-major residual -> staging -> own row
-      __syncwarp();
       if (F32_IN) {
+        if (row_valid) {                       // this thread's 32 fp32 channels: the whole 128-byte row of half tile `half`
+          const uint8_t* rp = xs + half * PAIR_X_TILE + (size_t)xrow * 128;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) stg_f[PSR_F(i)] = *reinterpret_cast<const float4*>(&xr[i]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 x = stg_f[PSO_F(i)];
-          v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          stg_h[PSR_H(i)] = xr[i];
-          stg_l[PSR_H(i)] = xr[4 + i];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 yh = stg_h[PSO_H(i)], yl = stg_l[PSO_H(i)];
-          const __half2* ph2 = reinterpret_cast<const __half2*>(&yh);
-          const __half2* pl2 = reinterpret_cast<const __half2*>(&yl);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 fh = __half22float2(ph2[k]), fl = __half22float2(pl2[k]);
-            v[8 * i + 2 * k] += fh.x + fl.x;
-            v[8 * i + 2 * k + 1] += fh.y + fl.y;
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(rp + (((uint32_t)i ^ sw) << 4));
+            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
           }
         }
-      }
-      if (j + 1 < n_local) load_resid(j + 1);   // in flight while this tile is packed and stored
-      if (want_f) {                             // x_new, fp32 stream of the stack
-        __syncwarp();
+      } else {
+        if (row_valid) {                       // 32 of the 64 fp16 channels of the hi and of the lo tile
+          const uint8_t* rh = xs + (size_t)xrow * 128;
+          const uint8_t* rl = rh + PAIR_X_TILE;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) stg_f[PSO_F(i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        __syncwarp();
-        float4* g = reinterpret_cast<float4*>(P.out_f32 + in_base + (long)f_row * C) + f_c16;    // the clip's own row pitch
+          for (int i = 0; i < 4; ++i) {
+            const uint4 yh = *reinterpret_cast<const uint4*>(rh + (((uint32_t)(half * 4 + i) ^ sw) << 4));
+            const uint4 yl = *reinterpret_cast<const uint4*>(rl + (((uint32_t)(half * 4 + i) ^ sw) << 4));
+            const __half2* ph2 = reinterpret_cast<const __half2*>(&yh);
+            const __half2* pl2 = reinterpret_cast<const __half2*>(&yl);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 fh = __half22float2(ph2[k]), fl = __half22float2(pl2[k]);
+              v[8 * i + 2 * k] += fh.x + fl.x;
+              v[8 * i + 2 * k + 1] += fh.y + fl.y;
+            }
+          }
+        }
+        e2_bar_sync();                         // the fp32 result overwrites the plane tiles other warps still read
+      }
+      if (want_f && row_valid) {               // x_new in place: fp32 half tile `half`
+        uint8_t* rp = xs + half * PAIR_X_TILE + (size_t)xrow * 128;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (row_ok(m0, wrow0 + 4 * i + f_row)) g[i * C] = stg_f[PSR_F(i)];
+          *reinterpret_cast<float4*>(rp + (((uint32_t)i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
-      {                                         // activated plane for the next pair / stage
-        uint32_t hi[16];
+      uint32_t hi[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a0 = fmaxf(v[2 * i], v[2 * i] * slope_out), a1 = fmaxf(v[2 * i + 1], v[2 * i + 1] * slope_out);
-          amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));     // every row is finite (H border rows are zeroed)
-          const __half2 hh = __floats2half2_rn(a0, a1);
-          hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) stg_h[PSO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-        __syncwarp();
-        uint4* g = reinterpret_cast<uint4*>(P.out_a + out_base + (long)h_row * C) + h_c16;
+      for (int i = 0; i < 16; ++i) {
+        const float a0 = fmaxf(v[2 * i], v[2 * i] * slope_out), a1 = fmaxf(v[2 * i + 1], v[2 * i + 1] * slope_out);
+        amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));     // every row is finite (H border rows are zeroed)
+        const __half2 hh = __floats2half2_rn(a0, a1);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      if (!mbar_wait(act_free, (j & 1) ^ 1, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }    // store (j-1) has read the tile
+      if (row_valid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (row_ok(m0, wrow0 + 8 * i + h_row)) g[i * C] = stg_h[PSR_H(i)];
+          *reinterpret_cast<uint4*>(act_row + (((uint32_t)(half * 4 + i) ^ sw) << 4)) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
       }
+      fence_proxy_async();                     // generic-proxy writes -> visible to the TMA store
+      mbar_arrive(out_ready + s);
     }
     if (!(amax <= 65504.f) && P.err) atomicCAS(P.err, 0, ERR_FP16_OVERFLOW);
-#undef PSO_H
-#undef PSR_H
-#undef PSO_F
-#undef PSR_F
+  } else {
+    // ------------------------------------------------------------------ store warp: x_new and the activated tile leave by TMA
+    if (elect_one()) {
+      bool ok = true;
+      for (int j = 0; j < n_local && ok; ++j) {
+        const int tile = blockIdx.x + j * gridDim.x;
+        const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
+        const int t0 = (tile - img * P.tiles_per_img) * PAIR_ROWS;
+        const int s = j & 1;
+        if (!mbar_wait(out_ready + s, (j >> 1) & 1, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+        const uint8_t* xs = x_base + s * PAIR_X_STAGE;
+        if (want_f) {                          // rows past the clip are clipped by the tensor map
+          tma_store_3d(&P.xo_map, xs, 0, t0, img);
+          tma_store_3d(&P.xo_map, xs + PAIR_X_TILE, 32, t0, img);
+        }
+        tma_store_3d(&P.ao_map, act_base, 0, P.out_row0 + t0, img);
+        tma_store_commit();
+        tma_store_wait_read();                 // shared memory has been read: hand the buffers back
+        mbar_arrive(x_empty + s);
+        mbar_arrive(act_free);
+      }
+      tma_store_wait_all();                    // global writes complete before the kernel ends
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -394,7 +395,7 @@ static cudaError_t launch_pair_t(const PairParams& p, cudaStream_t stream) {
 
 cudaError_t launch_pair_tc(const PairParams& p, cudaStream_t stream) {
   if (p.C != PAIR_C) return cudaErrorInvalidValue;
-  return p.resid_f32 ? launch_pair_t<true>(p, stream) : launch_pair_t<false>(p, stream);
+  return p.in_f32 ? launch_pair_t<true>(p, stream) : launch_pair_t<false>(p, stream);
 }
 
 }  // namespace vf
