@@ -26,12 +26,12 @@
 //        back IN PLACE and leaves by TMA store, as does the activated tile: no LDG / STG, no staging transposes.
 //
 // Warp roles (every wait is bounded, ptx.cuh):
-//   warp 0       TMA producer: ring of four A tap slots (16 KB each), two residual stages (2 x 16 KB each); both weight
-//                matrices (2 x 3 x 8 KB) are loaded once and stay resident
-//   warp 1       MMA issuer, software pipelined P1(j+1) before P2(j); 12 MMAs per phase, descriptors precomputed
+//   warp 0       TMA producer: ring of three A tap slots (16 KB each); both weight matrices (2 x 3 x 8 KB) are loaded once and
+//                stay resident
+//   warp 1       MMA issuer, readiness driven: P2(j) as soon as H(j) is written, P1 taps as they land
 //   warps 2-5    E1: accumulator 1 -> H
 //   warps 6-13   E2: accumulator 2 + residual tile -> x_new in place + activated tile
-//   warp 14      TMA stores of x_new / the activated tile, then hands the stage back to the producer
+//   warp 14      TMA stores of x_new / the activated tile and TMA loads of the residual tiles (three stages of 2 x 16 KB)
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -48,7 +48,8 @@ constexpr int PAIR_X_STAGE = 2 * PAIR_X_TILE;
 constexpr int PAIR_E1_WARPS = 4, PAIR_E2_WARPS = 8;
 constexpr int PAIR_E1_THREADS = 32 * PAIR_E1_WARPS, PAIR_E2_THREADS = 32 * PAIR_E2_WARPS;
 constexpr int PAIR_THREADS = 64 + PAIR_E1_THREADS + PAIR_E2_THREADS + 32;
-constexpr int PAIR_SMEM = 4 * PAIR_A_TAP + 6 * PAIR_W_TAP + PAIR_H_BUF + 2 * PAIR_X_STAGE + PAIR_X_TILE + 512 + 2 * PAIR_C * 4 + 1024;
+constexpr int PAIR_A_SLOTS = 3, PAIR_X_STAGES = 3;
+constexpr int PAIR_SMEM = PAIR_A_SLOTS * PAIR_A_TAP + 6 * PAIR_W_TAP + PAIR_H_BUF + PAIR_X_STAGES * PAIR_X_STAGE + PAIR_X_TILE + 512 + 2 * PAIR_C * 4;
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -67,27 +68,27 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
   constexpr uint32_t IDESC = make_idesc_f16(GEMM_BM, C);
   constexpr uint32_t DHI = make_smem_desc_hi(128);
 
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_base = smem;                                   // [4] tap slots of 128 x 128 B
-  uint8_t* w_base = a_base + 4 * PAIR_A_TAP;                // [Wa tap 0..2][Wb tap 0..2], 8 KB each
+  // 226.8 of the 227 KB a CTA may have: the swizzled tiles need a 1024-byte aligned base, which the declaration requests
+  // (no slack to align by hand); a misaligned base is reported instead of silently corrupting the swizzle
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_base = smem;                                   // [3] tap slots of 128 x 128 B
+  uint8_t* w_base = a_base + PAIR_A_SLOTS * PAIR_A_TAP;     // [Wa tap 0..2][Wb tap 0..2], 8 KB each
   uint8_t* h_base = w_base + 6 * PAIR_W_TAP;                // 136 x 128 B
-  uint8_t* x_base = h_base + PAIR_H_BUF;                    // [2 stages][2 half tiles] (fp32: channel halves; planes: hi, lo)
-  uint8_t* act_base = x_base + 2 * PAIR_X_STAGE;            // activated output tile, 126 x 128 B
+  uint8_t* x_base = h_base + PAIR_H_BUF;                    // [3 stages][2 half tiles] (fp32: channel halves; planes: hi, lo)
+  uint8_t* act_base = x_base + PAIR_X_STAGES * PAIR_X_STAGE;   // activated output tile, 126 x 128 B
   uint64_t* bars = reinterpret_cast<uint64_t*>(act_base + PAIR_X_TILE);
   uint64_t* w_full = bars;            // [1]
-  uint64_t* a_full = bars + 1;        // [4]
-  uint64_t* a_empty = bars + 5;       // [4]
-  uint64_t* acc1_full = bars + 9;     // [2]
-  uint64_t* acc1_empty = bars + 11;   // [2]
-  uint64_t* h_ready = bars + 13;      // [1]
-  uint64_t* h_free = bars + 14;       // [1]
-  uint64_t* acc2_full = bars + 15;    // [2]
-  uint64_t* acc2_empty = bars + 17;   // [2]
-  uint64_t* x_full = bars + 19;       // [2] residual stage loaded
-  uint64_t* x_empty = bars + 21;      // [2] ... stored / released (store warp)
-  uint64_t* out_ready = bars + 23;    // [2] E2 has finished the stage and the activated tile
-  uint64_t* act_free = bars + 25;     // [1] the activated tile has been read by its TMA store
+  uint64_t* a_full = bars + 1;        // [3]
+  uint64_t* a_empty = bars + 4;       // [3]
+  uint64_t* acc1_full = bars + 7;     // [2]
+  uint64_t* acc1_empty = bars + 9;    // [2]
+  uint64_t* h_ready = bars + 11;      // [1]
+  uint64_t* h_free = bars + 12;       // [1]
+  uint64_t* acc2_full = bars + 13;    // [2]
+  uint64_t* acc2_empty = bars + 15;   // [2]
+  uint64_t* x_full = bars + 17;       // [3] residual stage loaded
+  uint64_t* out_ready = bars + 20;    // [3] E2 has finished the stage and the activated tile
+  uint64_t* act_free = bars + 23;     // [1] the activated tile has been read by its TMA store
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
   float* s_bias_a = reinterpret_cast<float*>(bars + 32);   // [C] (16-byte aligned)
   float* s_bias_b = s_bias_a + C;                          // [C]
@@ -99,14 +100,14 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
   const bool want_f = P.out_f32 != 0;
 
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) atomicCAS(P.err, 0, ERR_PIPE_PRODUCER);     // see the declaration of smem
     mbar_init(w_full, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < PAIR_A_SLOTS; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc1_full + i, 1); mbar_init(acc1_empty + i, PAIR_E1_THREADS);
       mbar_init(acc2_full + i, 1); mbar_init(acc2_empty + i, PAIR_E2_THREADS);
-      mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1);
-      mbar_init(out_ready + i, PAIR_E2_THREADS);
     }
+    for (int i = 0; i < PAIR_X_STAGES; ++i) { mbar_init(x_full + i, 1); mbar_init(out_ready + i, PAIR_E2_THREADS); }
     mbar_init(h_ready, PAIR_E1_THREADS); mbar_init(h_free, 1);
     mbar_init(act_free, 1);
     fence_mbar_init();
@@ -135,30 +136,16 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
         tma_load_2d(w_base + (3 + t) * PAIR_W_TAP, &P.wb_map, w_full, t * C, 0);
       }
       bool ok = true;
-      uint32_t n = 0;                 // A tap counter: slot n & 3, phase (n >> 2) & 1
+      uint32_t sl = 0, ph = 0;        // A tap slot and its phase bit
       for (int j = 0; j < n_local && ok; ++j) {
         const int tile = blockIdx.x + j * gridDim.x;
         const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
-        const int t0 = (tile - img * P.tiles_per_img) * PAIR_ROWS;
-        const int m0 = t0 - 1;
-        for (int t = 0; t < 3 && ok; ++t, ++n) {
-          const uint32_t sl = n & 3u;
-          if (!mbar_wait(a_empty + sl, ((n >> 2) & 1u) ^ 1u, P.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
+        const int m0 = (tile - img * P.tiles_per_img) * PAIR_ROWS - 1;
+        for (int t = 0; t < 3; ++t) {
+          if (!mbar_wait(a_empty + sl, ph ^ 1u, P.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
           mbar_expect_tx(a_full + sl, PAIR_A_TAP);
           tma_load_3d(a_base + sl * PAIR_A_TAP, &P.a_map, a_full + sl, 0, m0 + (t - 1) * P.dil, img);
-        }
-        if (!ok) break;
-        // residual tile of rows t0 .. t0+125 (rows past the clip are zero filled; they are clipped again on the way out)
-        const int s = j & 1;
-        if (!mbar_wait(x_empty + s, ((j >> 1) & 1) ^ 1, P.err, ERR_PIPE_PRODUCER)) { ok = false; break; }
-        uint8_t* xs = x_base + s * PAIR_X_STAGE;
-        mbar_expect_tx(x_full + s, 2 * PAIR_ROWS * 128);
-        if (F32_IN) {
-          tma_load_3d(xs, &P.xin_map[0], x_full + s, 0, t0, img);                    // channels 0..31
-          tma_load_3d(xs + PAIR_X_TILE, &P.xin_map[0], x_full + s, 32, t0, img);     // channels 32..63
-        } else {
-          tma_load_3d(xs, &P.xin_map[0], x_full + s, 0, t0, img);                    // hi plane
-          tma_load_3d(xs + PAIR_X_TILE, &P.xin_map[1], x_full + s, 0, t0, img);      // lo plane
+          if (++sl == PAIR_A_SLOTS) { sl = 0; ph ^= 1u; }
         }
       }
     }
@@ -170,39 +157,46 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
       const uint32_t dw0 = make_smem_desc_lo(smem_u32(w_base));
       const uint32_t dh = make_smem_desc_lo(smem_u32(h_base));
       bool ok = mbar_wait(w_full, 0, P.err, ERR_PIPE_MMA);
-      uint32_t n = 0;
-      for (int j = 0; j <= n_local && ok; ++j) {
-        if (j < n_local) {          // ---- P1(j): conv_a into accumulator 1[b]
-          const int b = j & 1;
-          if (!mbar_wait(acc1_empty + b, ((j >> 1) & 1) ^ 1, P.err, ERR_PIPE_MMA)) { ok = false; break; }
-          const uint32_t d = tmem_base + b * C;
-          for (int t = 0; t < 3 && ok; ++t, ++n) {
-            const uint32_t sl = n & 3u;
-            if (!mbar_wait(a_full + sl, (n >> 2) & 1u, P.err, ERR_PIPE_MMA)) { ok = false; break; }
+      // Readiness-driven issue order: P2(j) goes as soon as H(j) is written, P1 taps go as they land - so a late tap of
+      // tile j+1 never holds back the accumulator the output warps are waiting for (ncu: 20 % of all samples there when
+      // P1(j+1) was issued unconditionally before P2(j)).
+      int j1 = 0, t1 = 0, j2 = 0;     // next P1 tile / tap, next P2 tile
+      uint32_t sl = 0, ph = 0, spins = 0;
+      while (j2 < n_local && ok) {
+        bool progressed = false;
+        if (j2 < j1) {                // ---- P2(j2): conv_b on H into accumulator 2[b]
+          const int b = j2 & 1;
+          if (mbar_try_wait(h_ready, j2 & 1) && mbar_try_wait(acc2_empty + b, ((j2 >> 1) & 1) ^ 1)) {
             tc_fence_after();
-            const uint32_t da = da0 + sl * (PAIR_A_TAP >> 4);
-            const uint32_t dw = dw0 + t * (PAIR_W_TAP >> 4);
+            const uint32_t d = tmem_base + 2 * C + b * C;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_lo(d, da + 2 * k, dw + 2 * k, DHI, IDESC, (t | k) ? 1u : 0u);
-            umma_commit(a_empty + sl);
+            for (int t = 0; t < 3; ++t)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)      // view of tap t starts at buffer row t
+                umma_f16_lo(d, dh + t * (128 >> 4) + 2 * k, dw0 + (3 + t) * (PAIR_W_TAP >> 4) + 2 * k, DHI, IDESC, (t | k) ? 1u : 0u);
+            umma_commit(acc2_full + b);
+            umma_commit(h_free);
+            ++j2;
+            progressed = true;
           }
-          if (!ok) break;
-          umma_commit(acc1_full + b);
         }
-        if (j >= 1) {               // ---- P2(j-1): conv_b on H into accumulator 2[b]
-          const int i = j - 1, b = i & 1;
-          if (!mbar_wait(h_ready, i & 1, P.err, ERR_PIPE_MMA)) { ok = false; break; }
-          if (!mbar_wait(acc2_empty + b, ((i >> 1) & 1) ^ 1, P.err, ERR_PIPE_MMA)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t d = tmem_base + 2 * C + b * C;
+        if (!progressed && j1 < n_local && j1 < j2 + 2) {      // ---- one tap of P1(j1): conv_a into accumulator 1[b]
+          const int b = j1 & 1;
+          if ((t1 > 0 || mbar_try_wait(acc1_empty + b, ((j1 >> 1) & 1) ^ 1)) && mbar_try_wait(a_full + sl, ph)) {
+            tc_fence_after();
+            const uint32_t d = tmem_base + b * C;
+            const uint32_t da = da0 + sl * (PAIR_A_TAP >> 4);
+            const uint32_t dw = dw0 + t1 * (PAIR_W_TAP >> 4);
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)      // view of tap t starts at buffer row t
-              umma_f16_lo(d, dh + t * (128 >> 4) + 2 * k, dw0 + (3 + t) * (PAIR_W_TAP >> 4) + 2 * k, DHI, IDESC, (t | k) ? 1u : 0u);
-          umma_commit(acc2_full + b);
-          umma_commit(h_free);
+            for (int k = 0; k < 4; ++k) umma_f16_lo(d, da + 2 * k, dw + 2 * k, DHI, IDESC, (t1 | k) ? 1u : 0u);
+            umma_commit(a_empty + sl);
+            if (++sl == PAIR_A_SLOTS) { sl = 0; ph ^= 1u; }
+            if (++t1 == 3) { umma_commit(acc1_full + b); t1 = 0; ++j1; }
+            progressed = true;
+          }
         }
+        if (progressed) spins = 0;
+        else if (++spins > (1u << 24)) { if (P.err) atomicCAS(P.err, 0, ERR_PIPE_MMA); ok = false; }
       }
     }
     __syncwarp();
@@ -276,11 +270,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
     float amax = 0.f;
     bool ok = true;
     uint8_t* act_row = act_base + (size_t)xrow * 128;
+    int s = 0;                                 // residual stage j % 3 and its phase bit
+    uint32_t sph = 0;
     for (int j = 0; j < n_local && ok; ++j) {
-      const int b = j & 1, s = j & 1;
+      const int b = j & 1;
       const uint32_t pj = (j >> 1) & 1;
       uint8_t* xs = x_base + s * PAIR_X_STAGE;
-      if (!mbar_wait(x_full + s, pj, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+      if (!mbar_wait(x_full + s, sph, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       if (!mbar_wait(acc2_full + b, pj, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
       tc_fence_after();
       float v[32];
@@ -344,18 +340,37 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
       }
       fence_proxy_async();                     // generic-proxy writes -> visible to the TMA store
       mbar_arrive(out_ready + s);
+      if (++s == PAIR_X_STAGES) { s = 0; sph ^= 1u; }
     }
     if (!(amax <= 65504.f) && P.err) atomicCAS(P.err, 0, ERR_FP16_OVERFLOW);
   } else {
-    // ------------------------------------------------------------------ store warp: x_new and the activated tile leave by TMA
+    // ------------------------------------------------------------------ residual / output warp: the residual tiles arrive and
+    // x_new / the activated tile leave by TMA.  The thread that sees a stage's store complete re-arms the stage itself (no
+    // hand-off to the producer); three stages cover the HBM round trip at ~1.5 us per tile.
     if (elect_one()) {
+      auto load_x = [&](int jj, int st) {       // residual tile of rows t0 .. t0+125 (rows past the clip are zero filled;
+        const int tile = blockIdx.x + jj * gridDim.x;      // they are clipped again on the way out)
+        const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
+        const int t0 = (tile - img * P.tiles_per_img) * PAIR_ROWS;
+        uint8_t* xs = x_base + st * PAIR_X_STAGE;
+        mbar_expect_tx(x_full + st, 2 * PAIR_ROWS * 128);
+        if (F32_IN) {
+          tma_load_3d(xs, &P.xin_map[0], x_full + st, 0, t0, img);                    // channels 0..31
+          tma_load_3d(xs + PAIR_X_TILE, &P.xin_map[0], x_full + st, 32, t0, img);     // channels 32..63
+        } else {
+          tma_load_3d(xs, &P.xin_map[0], x_full + st, 0, t0, img);                    // hi plane
+          tma_load_3d(xs + PAIR_X_TILE, &P.xin_map[1], x_full + st, 0, t0, img);      // lo plane
+        }
+      };
+      for (int j = 0; j < PAIR_X_STAGES && j < n_local; ++j) load_x(j, j);
       bool ok = true;
+      int s = 0;
+      uint32_t sph = 0;
       for (int j = 0; j < n_local && ok; ++j) {
         const int tile = blockIdx.x + j * gridDim.x;
         const int img = (int)fast_div_pair((uint32_t)tile, (uint32_t)P.tiles_per_img, P.magic_t);
         const int t0 = (tile - img * P.tiles_per_img) * PAIR_ROWS;
-        const int s = j & 1;
-        if (!mbar_wait(out_ready + s, (j >> 1) & 1, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
+        if (!mbar_wait(out_ready + s, sph, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
         const uint8_t* xs = x_base + s * PAIR_X_STAGE;
         if (want_f) {                          // rows past the clip are clipped by the tensor map
           tma_store_3d(&P.xo_map, xs, 0, t0, img);
@@ -363,9 +378,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
         }
         tma_store_3d(&P.ao_map, act_base, 0, P.out_row0 + t0, img);
         tma_store_commit();
-        tma_store_wait_read();                 // shared memory has been read: hand the buffers back
-        mbar_arrive(x_empty + s);
+        tma_store_wait_read();                 // shared memory has been read: the buffers may be reused
         mbar_arrive(act_free);
+        if (j + PAIR_X_STAGES < n_local) load_x(j + PAIR_X_STAGES, s);
+        if (++s == PAIR_X_STAGES) { s = 0; sph ^= 1u; }
       }
       tma_store_wait_all();                    // global writes complete before the kernel ends
     }
