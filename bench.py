@@ -216,6 +216,12 @@ def stage_roofline(prof, stage_ms, peaks, clips, n_samples, frames, ssr=False):
             per_clip = (SSR_GFLOP_PER_CLIP_T1024 if ssr else UNET_GFLOP_PER_CLIP_T1024) * tp / 1024
             e["survey_8d_gflop_per_clip"] = per_clip
             e["engine_vs_survey"] = fl / 1e9 / clips / per_clip
+            # SURVEY.md 8(d) secondary floor: weights once + input / output / skips written and read once per clip
+            e["survey_8d_hbm_floor_gb"] = (248.5e6 + clips * (0.52e6 + 0.51e6 + 2 * 31.8e6) * (tp / 1024) * (8.0 if ssr else 1.0)) / 1e9
+        else:
+            # weights (~130 MB) + 0.5 MB in + 1.77 MB out per clip - the stage is tensor-bound there; the
+            # `min_hbm_gb` above is THIS design's layer-by-layer traffic (activations round-trip through HBM between launches)
+            e["survey_8d_hbm_floor_gb"] = (130e6 + clips * 2.27e6 * (n_samples / 441000.0)) / 1e9
         out.append(e)
     return out
 

@@ -163,10 +163,13 @@ __global__ void __launch_bounds__(256) voc_condition_kernel(VocCondParams p) {
   }
   split_store8(p.out.hi, p.out.lo, ((size_t)b * p.Tv + tv) * 128 + g * 8, c);
 }
+// One CTA per clip, fixed reduction order: the scale amp_to_original_f applies (and with it every output sample) is
+// reproducible run to run (a multi-CTA atomicAdd version differed in the last bits between identical calls).
 __global__ void __launch_bounds__(256) band_energy_kernel(const float* tgt, const float* logest, int T, float* sums) {
-  const int b = blockIdx.y;
+  __shared__ float sh[2][8];
+  const int b = blockIdx.x;
   float st = 0.f, se = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T * 20; i += gridDim.x * blockDim.x) {
+  for (int i = threadIdx.x; i < T * 20; i += 256) {
     const size_t idx = ((size_t)b * T + i / 20) * 128 + 5 + i % 20;
     st += __ldg(tgt + idx);
     se += exp10f(fminf(__ldg(logest + idx), 5.f));
@@ -176,15 +179,18 @@ __global__ void __launch_bounds__(256) band_energy_kernel(const float* tgt, cons
     st += __shfl_xor_sync(0xffffffffu, st, o);
     se += __shfl_xor_sync(0xffffffffu, se, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(sums + 2 * b, st);
-    atomicAdd(sums + 2 * b + 1, se);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = st; sh[1][threadIdx.x >> 5] = se; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i]; c += sh[1][i]; }
+    sums[2 * b] = a;
+    sums[2 * b + 1] = c;
   }
 }
 cudaError_t launch_band_energy(const float* mel_target_lin, const float* logmel_est, int batch, int T, float* sums,
                                cudaStream_t stream) {
-  dim3 grid(8, batch);
-  band_energy_kernel<<<grid, 256, 0, stream>>>(mel_target_lin, logmel_est, T, sums);
+  band_energy_kernel<<<batch, 256, 0, stream>>>(mel_target_lin, logmel_est, T, sums);
   return cudaGetLastError();
 }
 

@@ -448,6 +448,13 @@ int load_unet(vf_ctx* ctx, const std::string& U, UnetW* w) {
   return VF_OK;
 }
 
+// Residual add of a vocoder stack as an identity tap (through the accumulator, no epilogue loads) up to this channel count;
+// above it the epilogue adds the hi/lo planes.  VF_TUNE_IDENT_MAXC overrides (read at weight-load AND plan-build time).
+int ident_max_c() {
+  if (const char* ov = getenv("VF_TUNE_IDENT_MAXC")) return atoi(ov);
+  return 128;
+}
+
 int load_vocoder(vf_ctx* ctx) {
   int rc;
   const vf_config& c = ctx->cfg;
@@ -472,7 +479,7 @@ int load_vocoder(vf_ctx* ctx) {
       const std::string p = "vocoder.res." + std::to_string(s) + "." + std::to_string(i);
       NEED(wa, p + ".a.weight"); NEED(ba, p + ".a.bias"); NEED(wb, p + ".b.weight"); NEED(bb, p + ".b.bias");
       rc = pack_conv1d(ctx, &ctx->voc_res_a[s][i], *wa, *ba); if (rc) return rc;
-      rc = pack_conv1d(ctx, &ctx->voc_res_b[s][i], *wb, *bb, (int)wb->shape[0] <= 128); if (rc) return rc;
+      rc = pack_conv1d(ctx, &ctx->voc_res_b[s][i], *wb, *bb, (int)wb->shape[0] <= ident_max_c()); if (rc) return rc;
     }
   }
   {
@@ -1201,7 +1208,7 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         b.label = "voc.res" + std::to_string(s) + "." + std::to_string(i) + ".b";
         std::vector<GemmTap> taps = taps1d(3, 1, cout, true);
         ASrc xsrc{xr[curx], (int)L, 0};
-        if (cout <= 128) {
+        if (cout <= ident_max_c()) {
           // load/store-bound stacks: x rides through the accumulator (identity weights, both planes) and the
           // epilogue issues no global loads
           taps.push_back(GemmTap{0, 1, 0, 0, cout, 1});
