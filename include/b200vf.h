@@ -200,7 +200,9 @@ VF_API int vf_check_errors(vf_ctx* ctx, void* stream);
  * "host_pipeline" (default 1, see vf_restore_host),
  * "validate_simt" (1: run every GEMM on the SIMT validation kernel instead of tcgen05 - tests only). */
 VF_API int vf_set_option(vf_ctx* ctx, const char* key, int value);
-/* Plans are cached per (path, batch, frames); the cache is bounded (see "plan_cache_mb"). */
+/* Plans are cached per (path, batch, frames); the cache is bounded (see "plan_cache_mb").  A batch whose plan would not fit
+ * the budget is processed in sub-batches through a smaller plan (same results: rows are independent); the *_stages accessors
+ * then only see the last sub-batch. */
 VF_API int vf_plan_cache_info(vf_ctx* ctx, int* n_plans, size_t* bytes, size_t* budget, int64_t* evicted);
 /* Number of kernels this context has launched since creation. */
 VF_API int64_t vf_launch_count(vf_ctx* ctx);

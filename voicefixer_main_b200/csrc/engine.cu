@@ -1534,6 +1534,30 @@ int check_ready(vf_ctx* ctx) {
 
 }  // namespace
 
+// A batch whose plan would not fit the plan budget is processed in sub-batches through one smaller plan (rows are
+// independent, so the result does not change): SSR at 64 x 10 s (143 GB) or a long file's stack of windows then run in two
+// or more passes instead of failing with an out-of-memory plan.  Workspace scales with batch x padded frames; the per-frame
+// figure is taken from a cached plan of the same path when there is one, else from the measured sizes.
+int choose_sub_batch(vf_ctx* ctx, int kind, int batch, int frames) {
+  if (ctx->plan_budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->plan_budget = std::max<size_t>((free_b + ctx->plan_bytes) / 2, (size_t)1 << 30);
+  }
+  const double tp = (frames + 63) / 64 * 64;
+  double per_frame = kind == PLAN_SSR ? 2.4e6 : 1.7e6;      // bytes per clip and padded frame (measured 2.19e6 / 1.52e6) + margin
+  for (auto& kv : ctx->plans)
+    if (std::get<0>(kv.first) == kind) {
+      per_frame = 1.05 * (double)kv.second->bytes / ((double)kv.second->batch * ((kv.second->T + 63) / 64 * 64));
+      break;
+    }
+  const double fit = (double)ctx->plan_budget / (per_frame * tp);
+  if (fit >= batch) return batch;
+  int cb = std::max(1, (int)fit);
+  for (int d = cb; d >= std::max(1, cb * 3 / 4); --d)         // prefer an even split (one plan shape instead of two)
+    if (batch % d == 0) return d;
+  return cb;
+}
+
 // =============================================================================================== C ABI
 extern "C" {
 
@@ -1736,7 +1760,12 @@ VF_API int vf_restore_ex(vf_ctx* ctx, const float* wav, int batch, int64_t n, fl
   if (rc) return rc;
   if (!wav || !wav_out || batch <= 0) return fail(ctx, VF_EINVAL, "vf_restore: bad arguments");
   if (flags & ~(unsigned)VF_RESTORE_UNIFY_ENERGY) return fail(ctx, VF_EINVAL, "vf_restore_ex: unknown flag bits 0x%x", flags);
-  return restore_impl(ctx, wav, batch, n, wav_out, flags, (cudaStream_t)stream);
+  const int cb = choose_sub_batch(ctx, PLAN_GSR, batch, frames_of(ctx, (long)n));
+  for (int off = 0; off < batch; off += cb) {
+    rc = restore_impl(ctx, wav + (size_t)off * n, std::min(cb, batch - off), n, wav_out + (size_t)off * n, flags, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return VF_OK;
 }
 
 VF_API int vf_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
@@ -1748,14 +1777,20 @@ VF_API int vf_restore_host(vf_ctx* ctx, const float* wav_host, int batch, int64_
   if (rc) return rc;
   if (!wav_host || !out_host || batch <= 0) return fail(ctx, VF_EINVAL, "vf_restore_host: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  Plan* plan;
-  rc = get_plan(ctx, PLAN_GSR, batch, frames_of(ctx, (long)n), &plan);
-  if (rc) return rc;
-  rc = ensure_io(ctx, plan, (long)n);
-  if (rc) return rc;
   const unsigned flags = ctx->unify_energy ? VF_RESTORE_UNIFY_ENERGY : 0u;
-  return host_roundtrip(ctx, plan, wav_host, out_host, (size_t)batch * n * 4, st,
-                        [&](const float* d_in, float* d_out, cudaStream_t s) { return restore_impl(ctx, d_in, batch, n, d_out, flags, s); });
+  const int cb = choose_sub_batch(ctx, PLAN_GSR, batch, frames_of(ctx, (long)n));
+  for (int off = 0; off < batch; off += cb) {
+    const int b = std::min(cb, batch - off);
+    Plan* plan;
+    rc = get_plan(ctx, PLAN_GSR, b, frames_of(ctx, (long)n), &plan);
+    if (rc) return rc;
+    rc = ensure_io(ctx, plan, (long)n);
+    if (rc) return rc;
+    rc = host_roundtrip(ctx, plan, wav_host + (size_t)off * n, out_host + (size_t)off * n, (size_t)b * n * 4, st,
+                        [&](const float* d_in, float* d_out, cudaStream_t s) { return restore_impl(ctx, d_in, b, n, d_out, flags, s); });
+    if (rc) return rc;
+  }
+  return VF_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- SSR / GSR-UNet path
@@ -1800,10 +1835,17 @@ VF_API int vf_ssr_forward(vf_ctx* ctx, const float* sp, const float* wav, int ba
   if (rc) return rc;
   if (!wav || !wav_out || batch <= 0) return fail(ctx, VF_EINVAL, "vf_ssr_forward: bad arguments");
   if (n <= 1024) return fail(ctx, VF_EINVAL, "reflect padding needs more than n_fft/2 = 1024 samples (got %ld)", (long)n);
-  Plan* plan;
-  rc = get_plan(ctx, PLAN_SSR, batch, frames_of(ctx, (long)n), &plan);
-  if (rc) return rc;
-  return ssr_impl(ctx, plan, sp, wav, batch, n, wav_out, (cudaStream_t)stream);
+  const int frames = frames_of(ctx, (long)n);
+  const int cb = choose_sub_batch(ctx, PLAN_SSR, batch, frames);
+  for (int off = 0; off < batch; off += cb) {
+    const int b = std::min(cb, batch - off);
+    Plan* plan;
+    rc = get_plan(ctx, PLAN_SSR, b, frames, &plan);
+    if (rc) return rc;
+    rc = ssr_impl(ctx, plan, sp ? sp + (size_t)off * frames * 1025 : nullptr, wav + (size_t)off * n, b, n, wav_out + (size_t)off * n, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return VF_OK;
 }
 
 VF_API int vf_ssr_restore(vf_ctx* ctx, const float* wav, int batch, int64_t n, float* wav_out, void* stream) {
@@ -1816,13 +1858,20 @@ VF_API int vf_ssr_restore_host(vf_ctx* ctx, const float* wav_host, int batch, in
   if (!wav_host || !out_host || batch <= 0) return fail(ctx, VF_EINVAL, "vf_ssr_restore_host: bad arguments");
   if (n <= 1024) return fail(ctx, VF_EINVAL, "reflect padding needs more than n_fft/2 = 1024 samples (got %ld)", (long)n);
   cudaStream_t st = (cudaStream_t)stream;
-  Plan* plan;
-  rc = get_plan(ctx, PLAN_SSR, batch, frames_of(ctx, (long)n), &plan);
-  if (rc) return rc;
-  rc = ensure_io(ctx, plan, (long)n);
-  if (rc) return rc;
-  return host_roundtrip(ctx, plan, wav_host, out_host, (size_t)batch * n * 4, st,
-                        [&](const float* d_in, float* d_out, cudaStream_t s) { return ssr_impl(ctx, plan, nullptr, d_in, batch, n, d_out, s); });
+  const int frames = frames_of(ctx, (long)n);
+  const int cb = choose_sub_batch(ctx, PLAN_SSR, batch, frames);
+  for (int off = 0; off < batch; off += cb) {
+    const int b = std::min(cb, batch - off);
+    Plan* plan;
+    rc = get_plan(ctx, PLAN_SSR, b, frames, &plan);
+    if (rc) return rc;
+    rc = ensure_io(ctx, plan, (long)n);
+    if (rc) return rc;
+    rc = host_roundtrip(ctx, plan, wav_host + (size_t)off * n, out_host + (size_t)off * n, (size_t)b * n * 4, st,
+                        [&](const float* d_in, float* d_out, cudaStream_t s) { return ssr_impl(ctx, plan, nullptr, d_in, b, n, d_out, s); });
+    if (rc) return rc;
+  }
+  return VF_OK;
 }
 
 VF_API int vf_ssr_unet(vf_ctx* ctx, const float* sp, int batch, int frames, float* mag_out, void* stream) {
