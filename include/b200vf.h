@@ -170,6 +170,11 @@ VF_API int vf_finalize(vf_ctx* ctx, const float* wav, int batch, int64_t len, in
  * i*up + n_taps/2] * wav[b,i]; taps = the caller's symmetric FIR (odd n_taps, device pointer), n_out = ceil(n*up/down). */
 VF_API int vf_resample_poly(vf_ctx* ctx, const float* wav, int batch, int64_t n_samples, int up, int down, const float* taps,
                             int n_taps, float* out, int64_t n_out, void* stream);
+/* amp_to_original_f (tools/utils.py:50-55; handler() applies it when meta["unify_energy"], eval_gsr_voicefixer.py:54-55) on
+ * linear mels [B,T,128]: mel_out = mel_est * (mean of mel_target over bins 5..24 / mean of mel_est over bins 5..24), per clip.
+ * vf_restore_ex fuses the same step into the restore chain (VF_RESTORE_UNIFY_ENERGY). */
+VF_API int vf_amp_to_original_f(vf_ctx* ctx, const float* mel_est, const float* mel_target, int batch, int frames, float* mel_out,
+                                void* stream);
 /* AudioMetrics.lsd (evaluation_proc/metrics.py:83-87): est, target [images, frames, bins] (non-log) -> out [images]. */
 VF_API int vf_lsd(vf_ctx* ctx, const float* est, const float* target, int images, int frames, int bins, float* out, void* stream);
 /* AudioMetrics.sispec (metrics.py:89-95) per batch item over n values -> out [batch] (the reference then averages over

@@ -19,7 +19,7 @@ EXPORTS = [
     "vf_to_log", "vf_from_log", "vf_to_pcm16", "vf_workspace_bytes", "vf_check_errors", "vf_set_option", "vf_launch_count",
     "vf_enable_stage_timing", "vf_stage_times", "vf_selftest_gemm", "vf_enable_op_timing", "vf_op_count", "vf_op_info",
     "vf_restore_ex", "vf_ssr_forward", "vf_ssr_restore", "vf_ssr_restore_host", "vf_ssr_unet", "vf_ssr_stages", "vf_istft",
-    "vf_mel", "vf_finalize", "vf_plan_cache_info", "vf_resample_poly", "vf_lsd", "vf_sispec", "vf_to_pcm16_ex",
+    "vf_mel", "vf_finalize", "vf_plan_cache_info", "vf_resample_poly", "vf_lsd", "vf_sispec", "vf_to_pcm16_ex", "vf_amp_to_original_f",
 ]
 VF_RESTORE_UNIFY_ENERGY = 1
 
@@ -104,6 +104,7 @@ def load_library():
     lib.vf_plan_cache_info.argtypes = [P, POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int64)]
     lib.vf_resample_poly.argtypes = [P, P, c_int, c_int64, c_int, c_int, P, c_int, P, c_int64, P]
     lib.vf_to_pcm16_ex.argtypes = [P, P, P, c_int64, c_int, P]
+    lib.vf_amp_to_original_f.argtypes = [P, P, P, c_int, c_int, P, P]
     lib.vf_lsd.argtypes = [P, P, P, c_int, c_int, c_int, P, P]
     lib.vf_sispec.argtypes = [P, P, P, c_int, c_int64, c_int, c_int, P, P]
     _lib = lib

@@ -194,6 +194,40 @@ cudaError_t launch_band_energy(const float* mel_target_lin, const float* logmel_
   return cudaGetLastError();
 }
 
+// amp_to_original_f (tools/utils.py:50-55) as a stand-alone op on linear mels [B, T, 128]: est * (mean_low(target) / mean_low(est)),
+// low band = mel bins [5, int(128 * 0.2)); one CTA per clip, fixed reduction order.
+__global__ void __launch_bounds__(256) amp_to_original_kernel(const float* __restrict__ est, const float* __restrict__ tgt, int T, float* __restrict__ out) {
+  __shared__ float sh[2][8];
+  __shared__ float ratio;
+  const int b = blockIdx.x;
+  const size_t base = (size_t)b * T * 128;
+  float st = 0.f, se = 0.f;
+  for (int i = threadIdx.x; i < T * 20; i += 256) {
+    const size_t idx = base + (size_t)(i / 20) * 128 + 5 + i % 20;
+    st += __ldg(tgt + idx);
+    se += __ldg(est + idx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    st += __shfl_xor_sync(0xffffffffu, st, o);
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = st; sh[1][threadIdx.x >> 5] = se; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += sh[0][i]; c += sh[1][i]; }
+    ratio = a / c;              // the 1 / (T * 20) of both means cancels
+  }
+  __syncthreads();
+  const float r = ratio;
+  for (size_t i = threadIdx.x; i < (size_t)T * 128; i += 256) out[base + i] = __ldg(est + base + i) * r;
+}
+cudaError_t launch_amp_to_original(const float* est, const float* tgt, int batch, int T, float* out, cudaStream_t stream) {
+  amp_to_original_kernel<<<batch, 256, 0, stream>>>(est, tgt, T, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_voc_condition(const VocCondParams& p, cudaStream_t stream) {
   const size_t total = (size_t)p.batch * p.Tv * 16;
   voc_condition_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);

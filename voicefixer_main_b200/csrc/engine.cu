@@ -1957,6 +1957,14 @@ VF_API int vf_resample_poly(vf_ctx* ctx, const float* wav, int batch, int64_t n,
   return VF_OK;
 }
 
+VF_API int vf_amp_to_original_f(vf_ctx* ctx, const float* mel_est, const float* mel_target, int batch, int frames, float* mel_out, void* stream) {
+  if (!ctx || !mel_est || !mel_target || !mel_out || batch <= 0 || frames <= 0) return ctx ? fail(ctx, VF_EINVAL, "vf_amp_to_original_f: bad arguments") : VF_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_amp_to_original(mel_est, mel_target, batch, frames, mel_out, (cudaStream_t)stream));
+  ctx->launches++;
+  return VF_OK;
+}
+
 VF_API int vf_lsd(vf_ctx* ctx, const float* est, const float* target, int images, int frames, int bins, float* out, void* stream) {
   if (!ctx || !est || !target || !out || images <= 0 || frames <= 0 || bins <= 0) return ctx ? fail(ctx, VF_EINVAL, "vf_lsd: bad arguments") : VF_EINVAL;
   CK(cudaSetDevice(ctx->device));

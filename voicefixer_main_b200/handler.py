@@ -94,8 +94,7 @@ def restore_array(mdl: VoiceFixer, wav_10k: np.ndarray, device, unify_energy: bo
             log_mel, mel_noisy = log_mel[:, None], mel_noisy[:, None]
             denoised = eng.from_log(log_mel)
             if unify_energy:                     # eval_gsr_voicefixer.py:54-55 (tools/utils.py:50-55) before the lsd
-                lo = slice(5, int(128 * 0.2))
-                denoised = denoised * (mel_noisy[..., lo].mean(dim=(2, 3)) / denoised[..., lo].mean(dim=(2, 3)))[..., None, None]
+                denoised = eng.amp_to_original_f(denoised[:, 0].contiguous(), mel_noisy[:, 0].contiguous())[:, None]
             metrics.update({
                 "mel-lsd": float(am.lsd(denoised.contiguous(), target_mel.contiguous())),
                 "mel-sispec": float(am.sispec(log_mel, target_mel.contiguous(), target_map=1)),             # in log scale

@@ -216,6 +216,16 @@ class Engine:
                                          ctypes.c_void_p(out[o0:].data_ptr()), _stream()))
         return out.view(*lead, t, 128).transpose(-1, -2)     # same memory layout as the reference's matmul result
 
+    def amp_to_original_f(self, mel_est: torch.Tensor, mel_target: torch.Tensor) -> torch.Tensor:
+        """tools/utils.py:50-55 on linear mels [B,T,128]: the estimate scaled to the target's low-band energy."""
+        mel_est, mel_target = _check_in(mel_est, self.device, "mel_est"), _check_in(mel_target, self.device, "mel_target")
+        b, t, m = mel_est.shape
+        assert m == 128 and mel_target.shape == mel_est.shape
+        out = torch.empty_like(mel_est)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.vf_amp_to_original_f(self.ctx, _ptr(mel_est), _ptr(mel_target), b, t, _ptr(out), _stream()))
+        return out
+
     def finalize(self, wav: torch.Tensor, n: int) -> torch.Tensor:
         """eval_gsr_voicefixer.py:68-72: per-clip peak normalise (if max|x| > 1) + trim_center to n samples."""
         wav = _check_in(wav, self.device, "wav")
