@@ -581,6 +581,18 @@ struct Builder {
     if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(pair: C=%d rows=%d box=%dx%d esize=%d) -> %d", C, rows, box_c, box_rows, esize, (int)r);
     return VF_OK;
   }
+  // epilogue TMA stores: fp16 plane(s) [ld, rows, image, plane], box 32 channels x 32 rows x 1 x planes, SWIZZLE_64B
+  int make_map_out4(CUtensorMap* m, const __half* hi, const __half* lo, int planes, int ld, int rows, size_t img_rows, int n_img) {
+    const size_t pstride = planes == 2 ? (size_t)(lo - hi) : (size_t)n_img * img_rows * ld;
+    cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)rows, (cuuint64_t)n_img, (cuuint64_t)planes};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)img_rows * ld * 2, (cuuint64_t)pstride * 2};
+    cuuint32_t box[4] = {32, 32, 1, (cuuint32_t)planes};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(out planes: ld=%d rows=%d planes=%d) -> %d", ld, rows, planes, (int)r);
+    return VF_OK;
+  }
   // 3-term operands: hi and lo planes in ONE box ([C, rows, image, plane] / [K, N, plane]) - half the TMA issues
   int make_map4(CUtensorMap* m, const __half* base, int C, int rows, int img_rows, int n_img, size_t plane_stride, int box_c, bool sw128, int box_rows) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_img, 2};
@@ -806,6 +818,31 @@ struct Builder {
       if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }
       tp.stages = stages;
       tp.ctas_per_sm = ctas;
+      // MAP_PLAIN outputs leave the epilogue's staging tiles by TMA store (gemm_tc.cu); VF_TUNE_TMA_STORE=0 keeps LDS + STG
+      {
+        const char* tenv = getenv("VF_TUNE_TMA_STORE");
+        const int want = tenv ? atoi(tenv) : 7;
+        GemmEpilogue& pe = pr.epi;
+        const int orows = pe.out_row0 + pe.rows_in;
+        pe.tma_out = 0;
+        if (pe.map == MAP_PLAIN && want) {
+          if ((want & 1) && terms == 3 && pe.out_raw && pe.raw_ld % 4 == 0) {
+            rc = make_map3_any(&tp.o_raw, pe.out_raw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pe.raw_ld, orows, (size_t)pe.out_img_rows, n_img, 32, 32);
+            if (rc) return;
+            pe.tma_out |= 1;
+          }
+          if ((want & 2) && pe.out_r.hi) {
+            rc = make_map_out4(&tp.o_r, pe.out_r.hi, pe.out_r.lo, 2, pe.out_r.ld, orows, (size_t)pe.out_img_rows, n_img);
+            if (rc) return;
+            pe.tma_out |= 2;
+          }
+          if ((want & 4) && pe.out_a.hi) {
+            rc = make_map_out4(&tp.o_a, pe.out_a.hi, pe.out_a.lo, terms == 3 ? 2 : 1, pe.out_a.ld, orows, (size_t)pe.out_img_rows, n_img);
+            if (rc) return;
+            pe.tma_out |= 4;
+          }
+        }
+      }
       const long total_tiles = (long)n_img * pr.m_tiles * (N / bn);
       tp.grid = (int)std::min<long>(total_tiles, (long)ctx->sm_count * ctas);
       tp.magic_n = gemm_tc_magic((uint32_t)(N / bn), (uint64_t)total_tiles);

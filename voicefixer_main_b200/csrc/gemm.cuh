@@ -84,6 +84,8 @@ struct GemmEpilogue {
   const float* head_in;  // residual input [n_img, head_T, Wp] added to the head (log-mel, gsr_voicefixer.py:90), or null
   float* head_out;       // [n_img, head_T, Wp]: bins 0..Wp-2 = head + bias (+ head_in), bin Wp-1 = 0 (+ head_in): F.pad, unet.py:99
   int head_T;
+  int tma_out;           // MAP_PLAIN layers: bit 0 out_raw, bit 1 out_r, bit 2 out_a leave the staging tiles by TMA store
+                         // (GemmTcParams::o_raw / o_r / o_a) instead of LDS + STG: half the LSU wavefronts of the store path
   int* err;
 };
 
@@ -100,6 +102,8 @@ struct GemmProblem {
 struct GemmTcParams {
   CUtensorMap a_hi[2], a_lo[2];   // [C, rows, n_img] fp16
   CUtensorMap b_hi, b_lo;         // [Ktot, N] fp16 (K-major)
+  CUtensorMap o_raw;              // fp32 [raw_ld, rows, n_img], box 32 x 32 x 1, SWIZZLE_128B (epilogue TMA stores, see tma_out)
+  CUtensorMap o_r, o_a;           // fp16 [ld, rows, n_img, planes], box 32 x 32 x 1 x planes, SWIZZLE_64B
   int stages;
   int tile_chunks; // BK-wide K chunks per output tile
   int seg_chunks;  // 3-term mode: chunks per accumulation segment (promotion to registers in between)

@@ -335,6 +335,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
 #define SR_H(i) (32 * (i) + sr_h0 + (sr_hx ^ ((h_row >> 1) & 3)))
 #define SO_F(i) (so_f0 + ((i) ^ so_fx))
 #define SR_F(i) (32 * (i) + sr_f0 + (f_c16 ^ ((4 * (i) + f_row) & 7)))
+    // TMA-store output path (MAP_PLAIN layers, e.tma_out): the staging tiles are written in the layouts SWIZZLE_128B (fp32,
+    // 128-byte rows) / SWIZZLE_64B (fp16, 64-byte rows) expect - chunk ^ (row & 7) and chunk ^ ((row >> 1) & 3) are exactly the
+    // SO_F / SO_H slots - so lane 0 hands a finished tile to the copy engine instead of the warp reading it back row-major and
+    // storing it with 12 STG per lane: half the LSU wavefronts of the store path, which bounds the narrow layers (ncu l1tex 60-86 %)
+    const int tma_out = (map == MAP_PLAIN) ? e.tma_out : 0;
+    bool st_pending = false;             // a TMA store of this warp may still be reading its staging tile (warp-uniform)
+    auto stg_release = [&]() {
+      if (st_pending) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        st_pending = false;
+      }
+    };
     int prev_n0 = -1, g = 0;
     float amax = 0.f;
     bool ok = true;
@@ -376,8 +389,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         ctw = r - cth * Wp;
       }
       // store this warp's staged 32 rows x 32 columns of fp16 (hi [+ lo]) row-major: 8 rows x 64 B per instruction
-      auto store_rows_h = [&](const OutPlane& op, const int co0, const bool two) {
-        if (map == MAP_PLAIN) {
+      auto store_rows_h = [&](const OutPlane& op, const int co0, const bool two, const CUtensorMap* tm) {
+        if (tm) {                         // staged tile(s) -> TMA store; rows past rows_in are clipped by the tensor map
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(tm, stg_h, op.c_off + co0, e.out_row0 + wrow0, img, 0);
+            tma_store_commit();
+          }
+          st_pending = true;
+        } else if (map == MAP_PLAIN) {
           const size_t o0 = (size_t)(obase + h_row) * op.ld + op.c_off + co0;   // one wide multiply per chunk
           uint4* ph = reinterpret_cast<uint4*>(op.hi + o0) + h_c16;
           uint4* pl = reinterpret_cast<uint4*>(op.lo + o0) + h_c16;
@@ -459,6 +480,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         }
         if (THREE && has_resid) {         // coalesced global -> staging -> own row (MAP_PLAIN only; fp32 streams exist in 3-term mode only)
           const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
+          stg_release();
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -476,6 +498,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
         }
         if (has_resid_planes) {           // residual stream kept as hi/lo planes: coalesced load, sum in fp32
+          stg_release();
           __syncwarp();
           if (PREFETCH) {                 // loaded one chunk ahead (see load_resid below): no exposed load latency
 #pragma unroll
@@ -518,9 +541,19 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
         if (THREE && want_raw) {          // fp32 output
+          stg_release();
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) stg_f[SO_F(i)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (tma_out & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&P.o_raw, stg_f, co0, e.out_row0 + wrow0, img);
+              tma_store_commit();
+            }
+            st_pending = true;
+          } else {
           __syncwarp();
           if (map == MAP_PLAIN) {
             float4* pr4 = reinterpret_cast<float4*>(e.out_raw + (size_t)(obase + f_row) * e.raw_ld + co0) + f_c16;
@@ -536,10 +569,12 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
                 reinterpret_cast<float4*>(e.out_raw + (size_t)ri.orow * e.raw_ld + co0)[f_c16] = stg_f[SR_F(i)];
             }
           }
+          }
         }
         if (want_r) {                     // raw hi/lo planes
           uint32_t hi[16], lo[16];
           pack_hi_lo(v, hi, lo);
+          stg_release();
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -547,7 +582,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
-          store_rows_h(e.out_r, co0, true);
+          store_rows_h(e.out_r, co0, true, (tma_out & 2) ? &P.o_r : nullptr);
         }
         if (has_head) {                   // fused 1x1 head (N == 32)
 #pragma unroll
@@ -581,6 +616,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
           uint32_t hi[16], lo[16];
           if (THREE) pack_hi_lo(v, hi, lo); else pack_hi(v, hi);
+          stg_release();
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -588,7 +624,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             if (THREE) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
-          store_rows_h(e.out_a, co0, THREE);
+          store_rows_h(e.out_a, co0, THREE, (tma_out & 4) ? &P.o_a : nullptr);
         }
       };
 
@@ -644,6 +680,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
       }
       if (THREE && half == 0) epilogue_head(e, img, r, head_acc);
     }
+    if (tma_out && lane == 0) tma_store_wait_all();      // this thread's bulk stores have completed before the CTA exits
     // NaN compares false against everything, inf exceeds the bound
     if (!(amax <= 65504.f) && e.err) atomicCAS(e.err, 0, ERR_FP16_OVERFLOW);
   }

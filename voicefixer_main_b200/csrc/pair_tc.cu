@@ -51,14 +51,6 @@ constexpr int PAIR_THREADS = 64 + PAIR_E1_THREADS + PAIR_E2_THREADS + 32;
 constexpr int PAIR_A_SLOTS = 3, PAIR_X_STAGES = 3;
 constexpr int PAIR_SMEM = PAIR_A_SLOTS * PAIR_A_TAP + 6 * PAIR_W_TAP + PAIR_H_BUF + PAIR_X_STAGES * PAIR_X_STAGE + PAIR_X_TILE + 512 + 2 * PAIR_C * 4;
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void e2_bar_sync() { asm volatile("bar.sync 2, %0;" ::"r"(PAIR_E2_THREADS) : "memory"); }
 }  // namespace
 
