@@ -26,7 +26,7 @@
 
 namespace vf {
 cudaError_t launch_gemm_tc(const GemmTcParams& p, int bn, int bk, cudaStream_t stream);
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int tile_chunks);
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int tile_chunks, int resid_tma = 0);
 int gemm_tc_max_ctas(int bn);
 uint32_t gemm_tc_magic(uint32_t d, uint64_t nmax);
 cudaError_t launch_pair_tc(const PairParams& p, cudaStream_t stream);
@@ -669,6 +669,10 @@ struct Builder {
       rc = fail(ctx, VF_EINVAL, "1-term GEMM with an affine / head / fp32 stream epilogue (3-term kernels only)");
       return;
     }
+    // epilogue residual by TMA (gemm_tc.cu): a second 4 KB tile per epilogue warp; VF_TUNE_TMA_RESID=0 keeps LDG + staging
+    const char* renv = getenv("VF_TUNE_TMA_RESID");
+    const int resid_tma = (!renv || atoi(renv) != 0) && !ctx->validate_simt && epi.map == MAP_PLAIN &&
+                          ((terms == 3 && epi.resid != nullptr) != (epi.resid_hi != nullptr)) ? 1 : 0;      // exactly one residual source
     int k = 0;
     for (auto& t : taps) {
       t.k_off = k;
@@ -717,7 +721,7 @@ struct Builder {
         // a grouped stage holds up to 3 weight tiles: keep the grouping only if a 2-deep ring still fits
         int gchunks = 0;
         for (auto& t : grouped) gchunks += t.nch / bk;
-        if (gm > 1 && gemm_tc_smem_bytes(bn, bk, 2, (terms == 3 || any_both) ? 2 : 1, terms, GEMM_BM + 2, gm, gchunks) <= (size_t)226 * 1024) {
+        if (gm > 1 && gemm_tc_smem_bytes(bn, bk, 2, (terms == 3 || any_both) ? 2 : 1, terms, GEMM_BM + 2, gm, gchunks, resid_tma) <= (size_t)226 * 1024) {
           taps.swap(grouped);
           gmax = gm;
         }
@@ -800,6 +804,7 @@ struct Builder {
         snprintf(key, sizeof key, "VF_TUNE_CTAS_%d_%d", bn, terms);
         if (const char* ov = getenv(key)) { if (k <= 1024) ctas = std::max(1, std::min(reg_limit, atoi(ov))); }
       }
+      tp.resid_tma = resid_tma;
       int stages = 0;
       for (; ctas >= 1; --ctas) {
         // accumulator buffers: four where TMEM allows (run-ahead of the MMA thread over the epilogue's output phase)
@@ -812,7 +817,7 @@ struct Builder {
         if (tp.tmem_cols * ctas > 512) continue;
         const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
         for (stages = 8; stages >= 2; --stages)
-          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, tp.tile_chunks) <= per_cta) break;
+          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, tp.tile_chunks, tp.resid_tma) <= per_cta) break;
         if (stages >= 2) break;
       }
       if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }
@@ -825,6 +830,11 @@ struct Builder {
         GemmEpilogue& pe = pr.epi;
         const int orows = pe.out_row0 + pe.rows_in;
         pe.tma_out = 0;
+        if (tp.resid_tma) {
+          if (terms == 3 && pe.resid) rc = make_map3_any(&tp.i_res, pe.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pe.resid_ld, pe.rows_in, (size_t)pe.rows_in, n_img, 32, 32);
+          else rc = make_map_out4(&tp.i_res, pe.resid_hi, pe.resid_lo, 2, pe.resid_ld, pe.rows_in, (size_t)pe.rows_in, n_img);
+          if (rc) return;
+        }
         if (pe.map == MAP_PLAIN && want) {
           if ((want & 1) && terms == 3 && pe.out_raw && pe.raw_ld % 4 == 0) {
             rc = make_map3_any(&tp.o_raw, pe.out_raw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pe.raw_ld, orows, (size_t)pe.out_img_rows, n_img, 32, 32);

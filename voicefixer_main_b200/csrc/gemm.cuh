@@ -102,6 +102,9 @@ struct GemmProblem {
 struct GemmTcParams {
   CUtensorMap a_hi[2], a_lo[2];   // [C, rows, n_img] fp16
   CUtensorMap b_hi, b_lo;         // [Ktot, N] fp16 (K-major)
+  CUtensorMap i_res;              // epilogue residual by TMA load (resid_tma): fp32 [resid_ld, rows_in, n_img] box 32 x 32 x 1
+                                  // SWIZZLE_128B (3-term), or fp16 planes [resid_ld, rows_in, n_img, 2] box 32 x 32 x 1 x 2 SWIZZLE_64B
+  int resid_tma;                  // 1: each epilogue warp owns a second 4 KB tile + an mbarrier for it
   CUtensorMap o_raw;              // fp32 [raw_ld, rows, n_img], box 32 x 32 x 1, SWIZZLE_128B (epilogue TMA stores, see tma_out)
   CUtensorMap o_r, o_a;           // fp16 [ld, rows, n_img, planes], box 32 x 32 x 1 x planes, SWIZZLE_64B
   int stages;

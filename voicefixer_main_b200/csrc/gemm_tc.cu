@@ -144,12 +144,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
   const int off_b = planes_a * a_slot;
   const int stage_bytes = off_b + P.gmax * B_SLOT;
   uint8_t* stg_base = smem + (size_t)stages * stage_bytes;          // EPI_WARPS x 4 KB staging
-  uint8_t* tail = stg_base + EPI_WARPS * 4096;
+  uint8_t* rstg_base = stg_base + EPI_WARPS * 4096;                  // resid_tma: EPI_WARPS x 4 KB residual tiles (TMA destination)
+  uint8_t* tail = rstg_base + (P.resid_tma ? EPI_WARPS * 4096 : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* seg_full_bar = empty_bar + stages;           // [nbuf <= 4] accumulator buffer holds a finished segment
   uint64_t* seg_empty_bar = seg_full_bar + 4;            // [nbuf <= 4] ... has been drained by every epilogue thread
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(seg_empty_bar + 4);   // keep the float arrays 16-byte aligned
+  uint64_t* resid_bar = seg_empty_bar + 4;               // [8] one per epilogue warp: its residual tile has landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(resid_bar + 8);   // keep the float arrays 16-byte aligned
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
   float* s_shift = s_scale + BN;                                // [BN]
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
       mbar_init(seg_full_bar + i, 1);
       mbar_init(seg_empty_bar + i, EPI_THREADS);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(resid_bar + i, 1);
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
     tma_prefetch_desc(&P.b_hi);
@@ -348,6 +351,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         st_pending = false;
       }
     };
+    // Residual by TMA (P.resid_tma): lane 0 asks the copy engine for the warp's next [32 rows x 32 columns] residual tile (fp32,
+    // or the hi and lo planes) while the current chunk is processed; the threads read their own rows from the swizzled tile.
+    // No LDG, no STS for the residual - the other half of the epilogue's LSU traffic (see tma_out above).
+    const bool resid_tma = P.resid_tma != 0 && map == MAP_PLAIN;
+    uint8_t* rstg = rstg_base + (size_t)ew * 4096;
+    uint64_t* rbar = resid_bar + ew;
+    uint32_t rph = 0;
     int prev_n0 = -1, g = 0;
     float amax = 0.f;
     bool ok = true;
@@ -441,7 +451,15 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
         }
       };
-      if (PREFETCH && has_resid_planes) load_resid(half);
+      auto issue_resid = [&](const int j) {      // one elected lane; the tile is complete when rbar flips
+        if (lane == 0) {
+          mbar_expect_tx(rbar, 4096);
+          if (has_resid) tma_load_3d(rstg, &P.i_res, rbar, n0 + j * 32, wrow0, img);     // fp32 stream; else the hi/lo planes (4-D map)
+          else tma_load_4d(rstg, &P.i_res, rbar, n0 + j * 32, wrow0, img, 0);
+        }
+      };
+      if (resid_tma) issue_resid(half);
+      else if (PREFETCH && has_resid_planes) load_resid(half);
 
       // One 32-column chunk of this thread's row: bias, residual, outputs (see gemm.cuh for the semantics).
       auto process_chunk = [&](const int j, float (&v)[32]) {
@@ -478,7 +496,18 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
           }
         }
-        if (THREE && has_resid) {         // coalesced global -> staging -> own row (MAP_PLAIN only; fp32 streams exist in 3-term mode only)
+        if (THREE && has_resid && resid_tma) {      // the tile was requested one chunk ago (or at the start of the tile)
+          if (!mbar_wait(rbar, rph, e.err, ERR_PIPE_EPILOGUE)) ok = false;
+          rph ^= 1u;
+          const float4* rt = reinterpret_cast<const float4*>(rstg);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = rt[SO_F(i)];
+            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          }
+          __syncwarp();                   // every lane has read the tile: it may be refilled
+          if (j + CHUNK_STEP < BN / 32) issue_resid(j + CHUNK_STEP);
+        } else if (THREE && has_resid) {         // coalesced global -> staging -> own row (MAP_PLAIN only; fp32 streams exist in 3-term mode only)
           const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
           stg_release();
           __syncwarp();
@@ -497,7 +526,26 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
           }
         }
-        if (has_resid_planes) {           // residual stream kept as hi/lo planes: coalesced load, sum in fp32
+        if (has_resid_planes && resid_tma) {
+          if (!mbar_wait(rbar, rph, e.err, ERR_PIPE_EPILOGUE)) ok = false;
+          rph ^= 1u;
+          const uint4* rth = reinterpret_cast<const uint4*>(rstg);
+          const uint4* rtl = rth + 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 xh = rth[SO_H(i)], xl = rtl[SO_H(i)];
+            const __half2* ph = reinterpret_cast<const __half2*>(&xh);
+            const __half2* pl = reinterpret_cast<const __half2*>(&xl);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 fh = __half22float2(ph[k]), fl = __half22float2(pl[k]);
+              v[8 * i + 2 * k] += fh.x + fl.x;
+              v[8 * i + 2 * k + 1] += fh.y + fl.y;
+            }
+          }
+          __syncwarp();
+          if (j + CHUNK_STEP < BN / 32) issue_resid(j + CHUNK_STEP);
+        } else if (has_resid_planes) {           // residual stream kept as hi/lo planes: coalesced load, sum in fp32
           stg_release();
           __syncwarp();
           if (PREFETCH) {                 // loaded one chunk ahead (see load_resid below): no exposed load latency
@@ -695,16 +743,16 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
 // ---------------------------------------------------------------------------------------------- host side
 static int epi_warps_for(int bn, int /*terms*/) { return bn == 32 ? 4 : 8; }
 
-size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int tile_chunks) {
+size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, int a_box_rows, int gmax, int tile_chunks, int resid_tma) {
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
   const size_t stage = planes_a * a_slot + (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2;
   const int ew = epi_warps_for(bn, terms);
-  return stages * stage + ew * 4096 + (2 * stages + 8) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + (size_t)tile_chunks * 16 + 1024;
+  return stages * stage + ew * 4096 * (resid_tma ? 2 : 1) + (2 * stages + 16) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + (size_t)tile_chunks * 16 + 1024;
 }
 
 template <int BN, int BK, int EW, bool THREE, int MINB>
 static cudaError_t launch_cfg(const GemmTcParams& p, cudaStream_t stream) {
-  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax, p.tile_chunks);
+  const size_t smem = gemm_tc_smem_bytes(BN, BK, p.stages, p.planes_a, p.prob.terms, p.a_box_rows, p.gmax, p.tile_chunks, p.resid_tma);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, EW, THREE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
