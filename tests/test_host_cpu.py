@@ -137,3 +137,18 @@ def test_resampler_filter_design_matches_scipy_firwin():
             c = m * down
             i = np.arange(max(0, -(-(c - half) // up)), min(len(x) - 1, (c + half) // up) + 1)
             assert abs(float(np.sum(ref[c - i * up + half] * x[i])) - y[m]) < 1e-9
+
+
+def test_pip_entry_points_refuse_what_is_not_built():
+    """signature-compatible restore / restore_inmem wrappers; no CPU path, mode 0 only."""
+    import numpy as np
+    from voicefixer_main_b200 import VoiceFixer
+    m = VoiceFixer()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.restore_inmem(np.zeros(100, np.float32), cuda=False, mode=0)
+    with pytest.raises(NotImplementedError):
+        m.restore_inmem(np.zeros(100, np.float32), cuda=True, mode=1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.restore("in.wav", "out.wav", cuda=False, mode=0)
+    with pytest.raises(RuntimeError):                        # not on a device yet
+        m.restore("in.wav", "out.wav")

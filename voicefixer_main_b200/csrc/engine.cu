@@ -50,6 +50,7 @@ struct GemmW {
   __half* lo = nullptr;
   float* bias = nullptr;
   int N = 0, K = 0;
+  int k_tail = 0;      // trailing identity block (pack_conv1d): a GEMM may contract the K - k_tail columns before it only
 };
 struct Affine {
   float* scale = nullptr;
@@ -340,6 +341,7 @@ int pack_conv1d(vf_ctx* ctx, GemmW* out, const HostT& w, const HostT& b, bool id
       for (int t = 0; t < k; ++t) m[(size_t)n * K + t * cin + c] = w.v[((size_t)n * cin + c) * k + t];
     if (identity) m[(size_t)n * K + k * cin + n] = 1.f;
   }
+  out->k_tail = identity ? cout : 0;
   return upload_gemm(ctx, out, m, cout, K, &b.v);
 }
 
@@ -730,7 +732,7 @@ struct Builder {
     // halo boxes: 128 + 2 rows; 3-term GEMMs fetch the hi and lo planes in one 4-D box, whose planes land back to
     // back in shared memory, so the box is grown to a whole number of 1024-byte swizzle atoms (136 / 144 rows)
     const int a_box_rows = gmax > 1 ? (terms == 3 ? (bk == 64 ? 136 : 144) : GEMM_BM + 2) : GEMM_BM;
-    if (k != W.K) { rc = fail(ctx, VF_EINVAL, "GEMM K mismatch: taps cover %d, packed weight has %d", k, W.K); return; }
+    if (k != W.K && k != W.K - W.k_tail) { rc = fail(ctx, VF_EINVAL, "GEMM K mismatch: taps cover %d, packed weight has %d", k, W.K); return; }
     GemmProblem pr;
     memset(&pr, 0, sizeof pr);
     pr.n_img = n_img;
@@ -847,7 +849,7 @@ struct Builder {
             pe.tma_out |= 2;
           }
           if ((want & 4) && pe.out_a.hi) {
-            rc = make_map_out4(&tp.o_a, pe.out_a.hi, pe.out_a.lo, terms == 3 ? 2 : 1, pe.out_a.ld, orows, (size_t)pe.out_img_rows, n_img);
+            rc = make_map_out4(&tp.o_a, pe.out_a.hi, pe.out_a.lo, (terms == 3 || pe.out_ar) ? 2 : 1, pe.out_a.ld, orows, (size_t)pe.out_img_rows, n_img);
             if (rc) return;
             pe.tma_out |= 4;
           }
@@ -877,12 +879,20 @@ struct Builder {
       const double out_elems = (double)n_img * (epi.map == MAP_CONVT1D ? (double)epi.out_rows_valid * epi.cout
                                                 : (epi.map == MAP_CONVT2D ? 4.0 * epi.rows_in * epi.cout : (double)epi.rows_in * N));
       op.bytes = a_bytes + (double)W.N * W.K * (terms == 3 ? 4 : 2) +
-                 out_elems * ((epi.out_raw ? 4 : 0) + (epi.out_r.hi ? 4 : 0) + (epi.out_a.hi ? (terms == 3 ? 4 : 2) : 0) + ((epi.resid || epi.resid_hi) ? 4 : 0));
+                 out_elems * ((epi.out_raw ? 4 : 0) + (epi.out_r.hi ? 4 : 0) + (epi.out_a.hi ? ((terms == 3 || epi.out_ar) ? 4 : 2) : 0) + ((epi.resid || epi.resid_hi) ? 4 : 0));
       snprintf(op.label, sizeof op.label, "%s", label.c_str());
     }
     ops.push_back(op);
   }
 };
+
+// (a, r) residual stream (gemm.cuh): fp16(1 / slope) in both halves of a word, 0 when the LeakyReLU is not invertible that way
+uint32_t ar_inv_word(float slope) {
+  if (!(slope > 0.f && slope <= 1.f)) return 0;
+  const __half h = __float2half(1.f / slope);
+  const uint32_t b = *reinterpret_cast<const unsigned short*>(&h);
+  return b == 0x7c00u ? 0u : (b | (b << 16));
+}
 
 GemmEpilogue epi_plain(int rows_in, int Wp, int cout, int out_img_rows) {
   GemmEpilogue e;
@@ -1158,8 +1168,14 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
     // (a tile reads rows up to `dil` away from the ones another CTA is writing), so the pairs ping-pong between xa and xa2.
     const char* fenv = getenv("VF_TUNE_FUSED_PAIR");
     const bool fused = !(fenv && atoi(fenv) == 0) && !ctx->validate_simt && terms == 1 && cout == 64;
+    // (a, r) residual stream of the hi-only mode (gemm.cuh): x lives in the activated plane the convs read anyway plus one
+    // fp16 correction plane (the otherwise unused lo plane of the same allocation), updated in place by every residual layer:
+    // 10 instead of 12 bytes per element through a two-launch pair, 8 instead of 12 through a fused pair.  VF_TUNE_AR_STREAM=0
+    // keeps separate hi/lo planes of x (and the fp32 stream of the fused stacks).
+    const char* aenv = getenv("VF_TUNE_AR_STREAM");
+    const uint32_t ar = (!(aenv && atoi(aenv) == 0) && !ctx->validate_simt && terms == 1) ? ar_inv_word(c.voc_res_slope) : 0u;
     // residual stream x as hi/lo planes (ping-pong; a fused stack only reads the first, written by the transposed conv)
-    Planes xr[2] = {b.planes(B, (int)L, cout), fused ? Planes() : b.planes(B, (int)L, cout)};
+    Planes xr[2] = {ar ? Planes() : b.planes(B, (int)L, cout), (fused || ar) ? Planes() : b.planes(B, (int)L, cout)};
     Planes xa = b.planes(B, (int)L, cout), ha = fused ? Planes() : b.planes(B, (int)L, cout);
     Planes tail_in;
     if (last_stage) tail_in = b.planes(B, (int)L + 6, cout);
@@ -1170,7 +1186,8 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
       e.map = MAP_CONVT1D; e.rows_in = (int)Lprev + 1; e.cout = cout; e.out_img_rows = (int)L; e.out_rows_valid = (int)L;
       e.ct_stride = sc; e.ct_pad = sc / 2 + sc % 2;
       e.bias = ctx->voc_up[s].bias;
-      e.out_r = OutPlane{xr[0].p.hi, xr[0].p.lo, cout, 0};
+      if (ar) e.out_ar = ar;
+      else e.out_r = OutPlane{xr[0].p.hi, xr[0].p.lo, cout, 0};
       set_out_a(e, xa, 0, nullptr, nullptr, ACT_LRELU, c.voc_res_slope);
       std::vector<GemmTap> taps = {GemmTap{0, 0, 0, 0, cin}, GemmTap{-1, 0, 0, 0, cin}};
       b.label = "voc.up" + std::to_string(s);
@@ -1181,8 +1198,10 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
     float* xf[2] = {nullptr, nullptr};       // fp32 residual stream of a fused stack (ping-pong)
     if (fused) {
       xa2 = b.planes(B, (int)L, cout);
-      xf[0] = b.alloc<float>((size_t)B * L * cout);
-      xf[1] = b.alloc<float>((size_t)B * L * cout);
+      if (!ar) {
+        xf[0] = b.alloc<float>((size_t)B * L * cout);
+        xf[1] = b.alloc<float>((size_t)B * L * cout);
+      }
     }
     if (b.rc) return b.rc;
     int cura = 0;
@@ -1204,14 +1223,22 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         pp.bias_a = ctx->voc_res_a[s][i].bias;
         pp.bias_b = ctx->voc_res_b[s][i].bias;
         const int orow0 = (last && last_stage) ? 3 : 0;
-        if (i == 0) {        // the stack's input: hi / lo planes written by the transposed conv above
+        if (ar) {            // (a, r) stream: the residual is rebuilt from the activated plane (an L2 hit: the centre tap just read
+          pp.ar_in = ar;     // these rows) and the correction plane; the new pair leaves as the two planes of `dst`
+          mrc = b.make_map3_any(&pp.xin_map[0], src.p.hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, (int)L, (size_t)src.img_rows, B, 64, 126);
+          if (!mrc) mrc = b.make_map3_any(&pp.xin_map[1], src.p.lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, (int)L, (size_t)src.img_rows, B, 64, 126);
+          if (!mrc && !last) {
+            pp.ar_out = ar;
+            mrc = b.make_map3_any(&pp.xo_map, dst.p.lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, (int)L, (size_t)dst.img_rows, B, 64, 126);
+          }
+        } else if (i == 0) {        // the stack's input: hi / lo planes written by the transposed conv above
           mrc = b.make_map3_any(&pp.xin_map[0], xr[0].p.hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, (int)L, (size_t)L, B, 64, 126);
           if (!mrc) mrc = b.make_map3_any(&pp.xin_map[1], xr[0].p.lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cout, (int)L, (size_t)L, B, 64, 126);
         } else {
           pp.in_f32 = 1;
           mrc = b.make_map3_any(&pp.xin_map[0], xf[curx], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, (int)L, (size_t)L, B, 32, 126);
         }
-        if (!mrc && !last) {
+        if (!mrc && !last && !ar) {
           pp.out_f32 = 1;
           mrc = b.make_map3_any(&pp.xo_map, xf[1 - curx], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cout, (int)L, (size_t)L, B, 32, 126);
         }
@@ -1231,7 +1258,8 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         pp.err = ctx->d_err;
         op.flops = 2.0 * 2.0 * (double)B * L * cout * 3.0 * cout;
         op.exec_flops = 2.0 * 2.0 * (double)B * pp.tiles_per_img * GEMM_BM * cout * 3.0 * cout;
-        op.bytes = (double)B * L * cout * (2 + 4 + (last ? 0 : 4) + 2);      // act in, x in, x_new out, act out
+        op.bytes = ar ? (double)B * L * cout * (2 + 2 + (last ? 0 : 2) + 2)    // act in (operand and residual), r in, r out, act out
+                      : (double)B * L * cout * (2 + 4 + (last ? 0 : 4) + 2);   // act in, x in, x_new out, act out
         snprintf(op.label, sizeof op.label, "voc.res%d.%d.pair", s, i);
         ops.push_back(op);
         curx = 1 - curx;
@@ -1250,12 +1278,20 @@ int build_vocoder(vf_ctx* ctx, Builder& b, Plan* plan) {
         GemmEpilogue e = epi_plain((int)L, 0, cout, dst.img_rows);
         e.out_row0 = (last && last_stage) ? 3 : 0;
         e.bias = ctx->voc_res_b[s][i].bias;
-        if (!last) e.out_r = OutPlane{xr[1 - curx].p.hi, xr[1 - curx].p.lo, cout, 0};
+        if (!last) {
+          if (ar) e.out_ar = ar;
+          else e.out_r = OutPlane{xr[1 - curx].p.hi, xr[1 - curx].p.lo, cout, 0};
+        }
         set_out_a(e, dst, 0, nullptr, nullptr, ACT_LRELU, last ? c.voc_stage_slope : c.voc_res_slope);
         b.label = "voc.res" + std::to_string(s) + "." + std::to_string(i) + ".b";
         std::vector<GemmTap> taps = taps1d(3, 1, cout, true);
         ASrc xsrc{xr[curx], (int)L, 0};
-        if (cout <= ident_max_c()) {
+        if (ar) {
+          // x = U(a) + r from the two planes of xa, rewritten in place: a tile reads exactly the rows it writes, and only
+          // the "a" conv of the next pair (a later launch) looks at neighbouring rows
+          e.resid_hi = xa.p.hi; e.resid_lo = xa.p.lo; e.resid_ld = cout; e.resid_ar = ar;
+          b.gemm(ops, ctx->voc_res_b[s][i], ASrc{ha, (int)L, 0}, nullptr, taps, e, B, terms);
+        } else if (cout <= ident_max_c()) {
           // load/store-bound stacks: x rides through the accumulator (identity weights, both planes) and the
           // epilogue issues no global loads
           taps.push_back(GemmTap{0, 1, 0, 0, cout, 1});

@@ -84,10 +84,31 @@ struct GemmEpilogue {
   const float* head_in;  // residual input [n_img, head_T, Wp] added to the head (log-mel, gsr_voicefixer.py:90), or null
   float* head_out;       // [n_img, head_T, Wp]: bins 0..Wp-2 = head + bias (+ head_in), bin Wp-1 = 0 (+ head_in): F.pad, unet.py:99
   int head_T;
+  // (a, r) residual stream of the hi-only vocoder stacks: x is kept as a = fp16(lrelu_s(x)) - the plane the next conv reads
+  // anyway - and r = fp16(x - U(a)), U(a) = min(a, a * inv) the inverse of the LeakyReLU (inv = fp16(1 / s), 0 < s <= 1, in
+  // both halves of these words; 0 = off).  Same ~22 significant bits as a hi/lo split of x itself, but a stack moves 4
+  // instead of 6 bytes per element out of every residual layer (no separate hi plane of x).
+  uint32_t resid_ar;     // the residual planes (resid_hi, resid_lo) hold (a, r): add U(a) + r
+  uint32_t out_ar;       // out_a is written as (hi plane = a, lo plane = r); 1-term kernels, ACT_LRELU, no affine
   int tma_out;           // MAP_PLAIN layers: bit 0 out_raw, bit 1 out_r, bit 2 out_a leave the staging tiles by TMA store
                          // (GemmTcParams::o_raw / o_r / o_a) instead of LDS + STG: half the LSU wavefronts of the store path
   int* err;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ __half2 ar_unact(const __half2 a, const uint32_t inv_bits) {
+  return __hmin2(a, __hmul2(a, *reinterpret_cast<const __half2*>(&inv_bits)));
+}
+// (a, r) of two values already activated to a0 = lrelu(v0), a1 = lrelu(v1)
+__device__ __forceinline__ void ar_split(const float v0, const float v1, const float a0, const float a1, const uint32_t inv_bits,
+                                         uint32_t& a_bits, uint32_t& r_bits) {
+  const __half2 a = __floats2half2_rn(a0, a1);
+  const float2 u = __half22float2(ar_unact(a, inv_bits));
+  const __half2 r = __floats2half2_rn(v0 - u.x, v1 - u.y);
+  a_bits = *reinterpret_cast<const uint32_t*>(&a);
+  r_bits = *reinterpret_cast<const uint32_t*>(&r);
+}
+#endif
 
 struct GemmProblem {
   int n_img;
@@ -133,6 +154,8 @@ struct PairParams {
   const float* bias_a;
   const float* bias_b;
   int in_f32, out_f32;
+  uint32_t ar_in, ar_out;        // (a, r) stream (see GemmEpilogue): xin_map = the activated and the correction plane of the source,
+                                 // xo_map = the correction plane of the destination (fp16, box 64 x 126 x 1); ar_out = 0 on the last pair
   int L, n_img, C, dil, out_img_rows, out_row0, tiles_per_img, stages, grid;
   uint32_t magic_t;              // gemm_tc_magic(tiles_per_img, ...)
   float slope_h, slope_out;

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     const bool has_resid = THREE && e.resid != nullptr, has_resid_planes = e.resid_hi != nullptr, has_head = THREE && e.head_w != nullptr;
     const int act = e.act;
     const float slope = e.slope;
+    const uint32_t resid_ar = THREE ? 0u : e.resid_ar, out_ar = THREE ? 0u : e.out_ar;      // (a, r) residual stream, gemm.cuh
     // lane roles for the row-major global accesses
     const int f_row = lane >> 3, f_c16 = lane & 7;       // fp32: 4 rows x 128 B per instruction
     const int h_row = lane >> 2, h_c16 = lane & 3;       // fp16: 8 rows x 64 B per instruction
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             const __half2* pl = reinterpret_cast<const __half2*>(&xl);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 fh = __half22float2(ph[k]), fl = __half22float2(pl[k]);
+              const float2 fh = __half22float2(resid_ar ? ar_unact(ph[k], resid_ar) : ph[k]), fl = __half22float2(pl[k]);
               v[8 * i + 2 * k] += fh.x + fl.x;
               v[8 * i + 2 * k + 1] += fh.y + fl.y;
             }
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             const __half2* pl = reinterpret_cast<const __half2*>(&xl);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 fh = __half22float2(ph[k]), fl = __half22float2(pl[k]);
+              const float2 fh = __half22float2(resid_ar ? ar_unact(ph[k], resid_ar) : ph[k]), fl = __half22float2(pl[k]);
               v[8 * i + 2 * k] += fh.x + fl.x;
               v[8 * i + 2 * k + 1] += fh.y + fl.y;
             }
@@ -647,7 +648,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
               v[4 * i + 2] = fmaf(v[4 * i + 2], a4.z, b4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], a4.w, b4.w);
             }
           }
-          if (act == ACT_LRELU) {           // slope in [0, 1]: max(a, slope * a)
+          uint32_t hi[16], lo[16];
+          if (out_ar) {                     // (a, r) stream: hi plane = fp16(lrelu(v)), lo plane = fp16(v - U(a)); |v| itself is range-checked
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float v0 = pad ? 0.f : v[2 * i], v1 = pad ? 0.f : v[2 * i + 1];
+              ar_split(v0, v1, fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope), out_ar, hi[i], lo[i]);
+            }
+          } else if (act == ACT_LRELU) {    // slope in [0, 1]: max(a, slope * a)
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], v[i] * slope);
           } else if (act == ACT_ELU) {
@@ -662,17 +670,17 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
 #pragma unroll
             for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
           }
-          uint32_t hi[16], lo[16];
-          if (THREE) pack_hi_lo(v, hi, lo); else pack_hi(v, hi);
+          if (THREE) pack_hi_lo(v, hi, lo);
+          else if (!out_ar) pack_hi(v, hi);
           stg_release();
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             stg_h[SO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            if (THREE) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            if (THREE || out_ar) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
           __syncwarp();
-          store_rows_h(e.out_a, co0, THREE, (tma_out & 4) ? &P.o_a : nullptr);
+          store_rows_h(e.out_a, co0, THREE || out_ar, (tma_out & 4) ? &P.o_a : nullptr);
         }
       };
 

@@ -54,8 +54,11 @@ constexpr int PAIR_SMEM = PAIR_A_SLOTS * PAIR_A_TAP + 6 * PAIR_W_TAP + PAIR_H_BU
 __device__ __forceinline__ void e2_bar_sync() { asm volatile("bar.sync 2, %0;" ::"r"(PAIR_E2_THREADS) : "memory"); }
 }  // namespace
 
-template <bool F32_IN>
+// MODE 0: residual in as hi/lo planes of x, out as fp32 (first pair of an fp32-stream stack); 1: fp32 in and out;
+// 2: the (a, r) stream of gemm.cuh - residual rebuilt from the activated plane + the correction plane, both out as fp16
+template <int MODE>
 __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_constant__ PairParams P) {
+  constexpr bool F32_IN = MODE == 1, AR = MODE == 2;
   constexpr int C = PAIR_C;
   constexpr uint32_t IDESC = make_idesc_f16(GEMM_BM, C);
   constexpr uint32_t DHI = make_smem_desc_hi(128);
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
     const int xrow = row_valid ? jrow - 1 : 0; // its row in the residual / output tiles
     const uint32_t sw = (uint32_t)(xrow & 7);  // SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
     const float slope_out = P.slope_out;
+    const uint32_t ar_in = P.ar_in, ar_out = P.ar_out;
     float amax = 0.f;
     bool ok = true;
     uint8_t* act_row = act_base + (size_t)xrow * 128;
@@ -302,13 +306,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
             const __half2* pl2 = reinterpret_cast<const __half2*>(&yl);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 fh = __half22float2(ph2[k]), fl = __half22float2(pl2[k]);
+              const float2 fh = __half22float2(AR ? ar_unact(ph2[k], ar_in) : ph2[k]), fl = __half22float2(pl2[k]);
               v[8 * i + 2 * k] += fh.x + fl.x;
               v[8 * i + 2 * k + 1] += fh.y + fl.y;
             }
           }
         }
-        e2_bar_sync();                         // the fp32 result overwrites the plane tiles other warps still read
+        if (!AR) e2_bar_sync();                // the fp32 result overwrites the plane tiles other warps still read
       }
       if (want_f && row_valid) {               // x_new in place: fp32 half tile `half`
         uint8_t* rp = xs + half * PAIR_X_TILE + (size_t)xrow * 128;
@@ -317,12 +321,28 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
           *reinterpret_cast<float4*>(rp + (((uint32_t)i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
       uint32_t hi[16];
+      if (AR && ar_out) {                      // x_new leaves as (a, r): the correction plane replaces the r tile in place - each
+        uint32_t lo[16];                       // thread rewrites exactly the 16-byte chunks it has just read
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a0 = fmaxf(v[2 * i], v[2 * i] * slope_out), a1 = fmaxf(v[2 * i + 1], v[2 * i + 1] * slope_out);
-        amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));     // every row is finite (H border rows are zeroed)
-        const __half2 hh = __floats2half2_rn(a0, a1);
-        hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        for (int i = 0; i < 16; ++i) {
+          const float v0 = v[2 * i], v1 = v[2 * i + 1];
+          amax = fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1)));   // |x| bounds |a| and keeps U(a) in range
+          ar_split(v0, v1, fmaxf(v0, v0 * slope_out), fmaxf(v1, v1 * slope_out), ar_out, hi[i], lo[i]);
+        }
+        if (row_valid) {
+          uint8_t* rl = xs + PAIR_X_TILE + (size_t)xrow * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(rl + (((uint32_t)(half * 4 + i) ^ sw) << 4)) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a0 = fmaxf(v[2 * i], v[2 * i] * slope_out), a1 = fmaxf(v[2 * i + 1], v[2 * i + 1] * slope_out);
+          amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));     // every row is finite (H border rows are zeroed)
+          const __half2 hh = __floats2half2_rn(a0, a1);
+          hi[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
       }
       if (!mbar_wait(act_free, (j & 1) ^ 1, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }    // store (j-1) has read the tile
       if (row_valid) {
@@ -364,7 +384,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
         const int t0 = (tile - img * P.tiles_per_img) * PAIR_ROWS;
         if (!mbar_wait(out_ready + s, sph, P.err, ERR_PIPE_EPILOGUE)) { ok = false; break; }
         const uint8_t* xs = x_base + s * PAIR_X_STAGE;
-        if (want_f) {                          // rows past the clip are clipped by the tensor map
+        if (AR) {
+          if (P.ar_out) tma_store_3d(&P.xo_map, xs + PAIR_X_TILE, 0, t0, img);      // correction plane, 64 fp16 channels
+        } else if (want_f) {                   // rows past the clip are clipped by the tensor map
           tma_store_3d(&P.xo_map, xs, 0, t0, img);
           tma_store_3d(&P.xo_map, xs + PAIR_X_TILE, 32, t0, img);
         }
@@ -389,21 +411,22 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
 
 size_t pair_tc_smem_bytes(int C, int /*stages*/) { return C == PAIR_C ? (size_t)PAIR_SMEM : 0; }
 
-template <bool F32_IN>
+template <int MODE>
 static cudaError_t launch_pair_t(const PairParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<F32_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(pair_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  pair_tc_kernel<F32_IN><<<p.grid, PAIR_THREADS, PAIR_SMEM, stream>>>(p);
+  pair_tc_kernel<MODE><<<p.grid, PAIR_THREADS, PAIR_SMEM, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pair_tc(const PairParams& p, cudaStream_t stream) {
   if (p.C != PAIR_C) return cudaErrorInvalidValue;
-  return p.in_f32 ? launch_pair_t<true>(p, stream) : launch_pair_t<false>(p, stream);
+  if (p.ar_in) return launch_pair_t<2>(p, stream);
+  return p.in_f32 ? launch_pair_t<1>(p, stream) : launch_pair_t<0>(p, stream);
 }
 
 }  // namespace vf

@@ -119,3 +119,60 @@ def handler(input, output, target, ckpt, device, needrefresh=False, meta={}):
     pcm = model._engine().to_pcm16(out[0], saturate=bool(meta.get("saturate", False)))
     save_pcm16(pcm.cpu().numpy(), fname=output, sample_rate=44100)
     return metrics
+
+
+# ---- the pip package's entry points (`VoiceFixer.restore(input, output, cuda, mode, your_vocoder_func)` /
+# `restore_inmem(wav_10k, cuda, mode, your_vocoder_func)`; the package is not in /root/reference - the signatures and the
+# 30 s segmentation follow the survey's description of it, mode 0 is the parity target)
+PIP_SEG_LENGTH = 44100 * 30
+
+
+def restore_inmem(mdl: VoiceFixer, wav_10k, cuda=True, mode=0, your_vocoder_func=None, unify_energy=True) -> np.ndarray:
+    """One in-memory 44.1 kHz file -> restored samples [1, N] (numpy), 30 s segments, each
+    pre -> analysis module -> from_log -> amp_to_original_f -> vocoder -> trim, concatenated.
+
+    All whole segments of the file go through ONE batched restore call (the segments are independent), the ragged last
+    one through a second.  cuda=False raises (there is no CPU path); mode 1 (pre low-pass) and mode 2 (train-mode
+    BatchNorm) are not built.  `your_vocoder_func(mel [B,1,T,128] linear) -> wav [B,1,L]` replaces stage C; the stages
+    then run one by one through the object protocol."""
+    if not cuda:
+        raise RuntimeError("restore_inmem: cuda=False is not available (there is no CPU path)")
+    if mode != 0:
+        raise NotImplementedError(f"restore_inmem: mode {mode} is not built (mode 0 only)")
+    if mdl.device is None:
+        raise RuntimeError("model is not on a CUDA device yet: call .to(device)")
+    wav = torch.as_tensor(np.ascontiguousarray(wav_10k, dtype=np.float32)).reshape(-1)
+    n = wav.shape[0]
+    if n == 0:
+        return np.zeros((1, 0), np.float32)
+    n_full = n // PIP_SEG_LENGTH
+    dev = wav.to(mdl.device)
+    res = []
+
+    def run(x):                                  # x [B, n_seg] on the device
+        if your_vocoder_func is None:
+            return mdl.restore(x, unify_energy=unify_energy)
+        eng = mdl._engine()
+        _, mel_noisy = mdl.pre(x[:, None])
+        denoised = eng.from_log(mdl(mel_noisy)["mel"])
+        if unify_energy:
+            denoised = eng.amp_to_original_f(denoised[:, 0].contiguous(), mel_noisy[:, 0].contiguous())[:, None]
+        out = your_vocoder_func(denoised)
+        return mdl.finalize(out.to(mdl.device, torch.float32).contiguous(), x.shape[1])[:, 0]
+
+    if n_full:
+        res.append(run(dev[:n_full * PIP_SEG_LENGTH].view(n_full, PIP_SEG_LENGTH)).reshape(1, -1))
+    if n > n_full * PIP_SEG_LENGTH:
+        res.append(run(dev[None, n_full * PIP_SEG_LENGTH:].contiguous()))
+    return torch.cat(res, -1).cpu().numpy()
+
+
+def restore_file(mdl: VoiceFixer, input, output, cuda=True, mode=0, your_vocoder_func=None):
+    """The package's `restore(input, output, cuda, mode, your_vocoder_func)`: wav file in, 16-bit 44.1 kHz wav out."""
+    if not cuda:
+        raise RuntimeError("restore: cuda=False is not available (there is no CPU path)")
+    if mdl.device is None:
+        raise RuntimeError("model is not on a CUDA device yet: call .to(device)")
+    wav_10k = load_wav(input, sample_rate=44100, engine=mdl._engine())
+    out = restore_inmem(mdl, wav_10k, cuda=cuda, mode=mode, your_vocoder_func=your_vocoder_func)
+    save_wave(out, fname=output, sample_rate=44100)

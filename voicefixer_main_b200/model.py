@@ -598,11 +598,24 @@ class VoiceFixer(_EngineModel):
         return self.forward(mel_orig)
 
     # ---- batched fused path
-    def restore(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None, unify_energy: bool = False) -> torch.Tensor:
+    def restore(self, wav, out=None, unify_energy: bool = False, **pip_kwargs):
         """wav [B,N] fp32 on device -> restored [B,N]; one 60 s-or-shorter segment per row.
         unify_energy: apply amp_to_original_f (tools/utils.py:50-55) as handler() does for the SSR test sets
-        (a per-call flag of vf_restore_ex: no context state is touched)."""
+        (a per-call flag of vf_restore_ex: no context state is touched).
+
+        Called with file paths - `restore(input="in.wav", output="out.wav", cuda=True, mode=0, your_vocoder_func=None)` -
+        it is the pip package's file entry point (handler.restore_file)."""
+        if isinstance(wav, (str, bytes)) or hasattr(wav, "__fspath__"):
+            from .handler import restore_file
+            return restore_file(self, wav, out if out is not None else pip_kwargs.pop("output"), **pip_kwargs)
+        if pip_kwargs:
+            raise TypeError(f"restore(tensor): unexpected arguments {sorted(pip_kwargs)}")
         return self._engine().restore(wav, out, unify_energy=unify_energy)
+
+    def restore_inmem(self, wav_10k, cuda=True, mode=0, your_vocoder_func=None):
+        """The pip package's in-memory entry point: 44.1 kHz samples -> restored [1, N] numpy (handler.restore_inmem)."""
+        from .handler import restore_inmem
+        return restore_inmem(self, wav_10k, cuda=cuda, mode=mode, your_vocoder_func=your_vocoder_func)
 
     def restore_host(self, wav_host: torch.Tensor, out_host: torch.Tensor):
         self._engine().restore_host(wav_host, out_host)
