@@ -671,10 +671,12 @@ struct Builder {
       rc = fail(ctx, VF_EINVAL, "1-term GEMM with an affine / head / fp32 stream epilogue (3-term kernels only)");
       return;
     }
-    // epilogue residual by TMA (gemm_tc.cu): a second 4 KB tile per epilogue warp; VF_TUNE_TMA_RESID=0 keeps LDG + staging
+    // epilogue residual by TMA (gemm_tc.cu): one or two more 4 KB tiles per epilogue warp, requested that many chunks ahead;
+    // VF_TUNE_TMA_RESID=0 keeps LDG + staging, =1 pins one tile in flight (default: two where the operand ring keeps its depth)
     const char* renv = getenv("VF_TUNE_TMA_RESID");
-    const int resid_tma = (!renv || atoi(renv) != 0) && !ctx->validate_simt && epi.map == MAP_PLAIN &&
-                          ((terms == 3 && epi.resid != nullptr) != (epi.resid_hi != nullptr)) ? 1 : 0;      // exactly one residual source
+    const int resid_want = renv ? std::max(0, std::min(2, atoi(renv))) : 2;
+    const int resid_tma = (resid_want && !ctx->validate_simt && epi.map == MAP_PLAIN &&
+                           ((terms == 3 && epi.resid != nullptr) != (epi.resid_hi != nullptr))) ? 1 : 0;      // exactly one residual source
     int k = 0;
     for (auto& t : taps) {
       t.k_off = k;
@@ -818,9 +820,19 @@ struct Builder {
         tp.tmem_cols = pow2((1 << nb_log) * acc_w);
         if (tp.tmem_cols * ctas > 512) continue;
         const size_t per_cta = (size_t)227 * 1024 / ctas - 1024;
-        for (stages = 8; stages >= 2; --stages)
-          if (gemm_tc_smem_bytes(bn, bk, stages, tp.planes_a, terms, a_box_rows, gmax, tp.tile_chunks, tp.resid_tma) <= per_cta) break;
+        auto fit = [&](int ring) {
+          int st = 8;
+          for (; st >= 2; --st)
+            if (gemm_tc_smem_bytes(bn, bk, st, tp.planes_a, terms, a_box_rows, gmax, tp.tile_chunks, ring) <= per_cta) break;
+          return st;
+        };
+        stages = fit(tp.resid_tma);
+        if (tp.resid_tma == 1 && resid_want == 2) {      // a second residual tile in flight if the operand ring stays deep enough
+          const int st2 = fit(2);
+          if (st2 >= 2 && (st2 == stages || st2 >= 4)) { tp.resid_tma = 2; stages = st2; }
+        }
         if (stages >= 2) break;
+        tp.resid_tma = resid_tma;
       }
       if (ctas < 1 || stages < 2) { rc = fail(ctx, VF_EINVAL, "no tcgen05 tile configuration fits (bn=%d bk=%d terms=%d)", bn, bk, terms); return; }
       tp.stages = stages;

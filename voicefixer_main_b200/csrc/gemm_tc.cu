@@ -145,13 +145,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
   const int stage_bytes = off_b + P.gmax * B_SLOT;
   uint8_t* stg_base = smem + (size_t)stages * stage_bytes;          // EPI_WARPS x 4 KB staging
   uint8_t* rstg_base = stg_base + EPI_WARPS * 4096;                  // resid_tma: EPI_WARPS x 4 KB residual tiles (TMA destination)
-  uint8_t* tail = rstg_base + (P.resid_tma ? EPI_WARPS * 4096 : 0);
+  uint8_t* tail = rstg_base + (size_t)P.resid_tma * EPI_WARPS * 4096;  // P.resid_tma = tiles in flight per warp (0, 1 or 2)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* seg_full_bar = empty_bar + stages;           // [nbuf <= 4] accumulator buffer holds a finished segment
   uint64_t* seg_empty_bar = seg_full_bar + 4;            // [nbuf <= 4] ... has been drained by every epilogue thread
-  uint64_t* resid_bar = seg_empty_bar + 4;               // [8] one per epilogue warp: its residual tile has landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(resid_bar + 8);   // keep the float arrays 16-byte aligned
+  uint64_t* resid_bar = seg_empty_bar + 4;               // [8][2] per epilogue warp and ring slot: the residual tile has landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(resid_bar + 16);   // keep the float arrays 16-byte aligned
   float* s_bias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN]  (16-byte aligned: float4 reads)
   float* s_scale = s_bias + BN;                                // [BN]
   float* s_shift = s_scale + BN;                                // [BN]
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
       mbar_init(seg_full_bar + i, 1);
       mbar_init(seg_empty_bar + i, EPI_THREADS);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(resid_bar + i, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(resid_bar + i, 1);
     fence_mbar_init();
     tma_prefetch_desc(&P.a_hi[0]);
     tma_prefetch_desc(&P.b_hi);
@@ -352,13 +352,34 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
         st_pending = false;
       }
     };
-    // Residual by TMA (P.resid_tma): lane 0 asks the copy engine for the warp's next [32 rows x 32 columns] residual tile (fp32,
-    // or the hi and lo planes) while the current chunk is processed; the threads read their own rows from the swizzled tile.
-    // No LDG, no STS for the residual - the other half of the epilogue's LSU traffic (see tma_out above).
-    const bool resid_tma = P.resid_tma != 0 && map == MAP_PLAIN;
-    uint8_t* rstg = rstg_base + (size_t)ew * 4096;
-    uint64_t* rbar = resid_bar + ew;
-    uint32_t rph = 0;
+    // Residual by TMA (P.resid_tma): lane 0 asks the copy engine for the warp's next [32 rows x 32 columns] residual tiles (fp32,
+    // or the hi and lo planes) while earlier chunks are processed; the threads read their own rows from the swizzled tile.
+    // No LDG, no STS for the residual - the other half of the epilogue's LSU traffic (see tma_out above).  The requests run
+    // P.resid_tma (1 or 2) chunks ahead ACROSS tiles: a warp's chunk sequence is known up front (persistent tile loop), and a
+    // request issued only at the start of its own tile exposes one HBM round trip per tile (ncu on voc.res2.*.b: 4.8 us per
+    // 2-chunk tile, every unit below 62 %).
+    const int resid_ring = (map == MAP_PLAIN) ? P.resid_tma : 0;
+    const bool resid_tma = resid_ring != 0;
+    uint8_t* rstg = rstg_base + (size_t)ew * resid_ring * 4096;
+    uint64_t* rbar = resid_bar + ew * 2;
+    uint32_t r_cons = 0, r_issued = 0;       // chunks consumed / requested by this warp
+    int pf_tile = blockIdx.x, pf_j = half;   // next chunk to request
+    auto issue_resid = [&]() {               // warp-uniform control flow, one lane issues
+      if (pf_tile >= total_tiles) return;
+      if (lane == 0) {
+        const TileCoord pt((uint32_t)pf_tile, P, n_tiles, pr.m_tiles);
+        const uint32_t slot = r_issued & (uint32_t)(resid_ring - 1);
+        uint8_t* dst = rstg + slot * 4096;
+        mbar_expect_tx(rbar + slot, 4096);
+        if (THREE && e.resid != nullptr) tma_load_3d(dst, &P.i_res, rbar + slot, pt.nt * BN + pf_j * 32, pt.mi * GEMM_BM + q * 32, pt.img);   // fp32 stream
+        else tma_load_4d(dst, &P.i_res, rbar + slot, pt.nt * BN + pf_j * 32, pt.mi * GEMM_BM + q * 32, pt.img, 0);                        // hi / lo planes
+      }
+      ++r_issued;
+      pf_j += CHUNK_STEP;
+      if (pf_j >= BN / 32) { pf_j = half; pf_tile += gridDim.x; }
+    };
+    if (resid_tma && half < BN / 32)
+      for (int i = 0; i < resid_ring; ++i) issue_resid();
     int prev_n0 = -1, g = 0;
     float amax = 0.f;
     bool ok = true;
@@ -452,15 +473,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
         }
       };
-      auto issue_resid = [&](const int j) {      // one elected lane; the tile is complete when rbar flips
-        if (lane == 0) {
-          mbar_expect_tx(rbar, 4096);
-          if (has_resid) tma_load_3d(rstg, &P.i_res, rbar, n0 + j * 32, wrow0, img);     // fp32 stream; else the hi/lo planes (4-D map)
-          else tma_load_4d(rstg, &P.i_res, rbar, n0 + j * 32, wrow0, img, 0);
-        }
-      };
-      if (resid_tma) issue_resid(half);
-      else if (PREFETCH && has_resid_planes) load_resid(half);
+      if (!resid_tma && PREFETCH && has_resid_planes) load_resid(half);
 
       // One 32-column chunk of this thread's row: bias, residual, outputs (see gemm.cuh for the semantics).
       auto process_chunk = [&](const int j, float (&v)[32]) {
@@ -498,16 +511,17 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
         }
         if (THREE && has_resid && resid_tma) {      // the tile was requested one chunk ago (or at the start of the tile)
-          if (!mbar_wait(rbar, rph, e.err, ERR_PIPE_EPILOGUE)) ok = false;
-          rph ^= 1u;
-          const float4* rt = reinterpret_cast<const float4*>(rstg);
+          const uint32_t slot = r_cons & (uint32_t)(resid_ring - 1);
+          if (!mbar_wait(rbar + slot, (r_cons >> (resid_ring >> 1)) & 1u, e.err, ERR_PIPE_EPILOGUE)) ok = false;
+          ++r_cons;
+          const float4* rt = reinterpret_cast<const float4*>(rstg + slot * 4096);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 x = rt[SO_F(i)];
             v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
           }
           __syncwarp();                   // every lane has read the tile: it may be refilled
-          if (j + CHUNK_STEP < BN / 32) issue_resid(j + CHUNK_STEP);
+          issue_resid();                  // the slot just read is free again: request the chunk `resid_ring` ahead
         } else if (THREE && has_resid) {         // coalesced global -> staging -> own row (MAP_PLAIN only; fp32 streams exist in 3-term mode only)
           const size_t rbase = ((size_t)img * rows_in + m0 + q * 32) * e.resid_ld + co0;
           stg_release();
@@ -528,9 +542,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
         }
         if (has_resid_planes && resid_tma) {
-          if (!mbar_wait(rbar, rph, e.err, ERR_PIPE_EPILOGUE)) ok = false;
-          rph ^= 1u;
-          const uint4* rth = reinterpret_cast<const uint4*>(rstg);
+          const uint32_t slot = r_cons & (uint32_t)(resid_ring - 1);
+          if (!mbar_wait(rbar + slot, (r_cons >> (resid_ring >> 1)) & 1u, e.err, ERR_PIPE_EPILOGUE)) ok = false;
+          ++r_cons;
+          const uint4* rth = reinterpret_cast<const uint4*>(rstg + slot * 4096);
           const uint4* rtl = rth + 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -545,7 +560,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             }
           }
           __syncwarp();
-          if (j + CHUNK_STEP < BN / 32) issue_resid(j + CHUNK_STEP);
+          issue_resid();                  // the slot just read is free again: request the chunk `resid_ring` ahead
         } else if (has_resid_planes) {           // residual stream kept as hi/lo planes: coalesced load, sum in fp32
           stg_release();
           __syncwarp();
@@ -755,7 +770,7 @@ size_t gemm_tc_smem_bytes(int bn, int bk, int stages, int planes_a, int terms, i
   const size_t a_slot = ((size_t)a_box_rows * bk * 2 + 1023) & ~(size_t)1023;
   const size_t stage = planes_a * a_slot + (size_t)gmax * (terms == 3 ? 2 : 1) * bn * bk * 2;
   const int ew = epi_warps_for(bn, terms);
-  return stages * stage + ew * 4096 * (resid_tma ? 2 : 1) + (2 * stages + 16) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + (size_t)tile_chunks * 16 + 1024;
+  return stages * stage + ew * 4096 * (1 + resid_tma) + (2 * stages + 24) * 8 + 32 + (3 * bn + 32) * 4 + ew * 32 * 8 + (size_t)tile_chunks * 16 + 1024;
 }
 
 template <int BN, int BK, int EW, bool THREE, int MINB>
