@@ -95,21 +95,6 @@ struct GemmEpilogue {
   int* err;
 };
 
-#ifdef __CUDACC__
-__device__ __forceinline__ __half2 ar_unact(const __half2 a, const uint32_t inv_bits) {
-  return __hmin2(a, __hmul2(a, *reinterpret_cast<const __half2*>(&inv_bits)));
-}
-// (a, r) of two values already activated to a0 = lrelu(v0), a1 = lrelu(v1)
-__device__ __forceinline__ void ar_split(const float v0, const float v1, const float a0, const float a1, const uint32_t inv_bits,
-                                         uint32_t& a_bits, uint32_t& r_bits) {
-  const __half2 a = __floats2half2_rn(a0, a1);
-  const float2 u = __half22float2(ar_unact(a, inv_bits));
-  const __half2 r = __floats2half2_rn(v0 - u.x, v1 - u.y);
-  a_bits = *reinterpret_cast<const uint32_t*>(&a);
-  r_bits = *reinterpret_cast<const uint32_t*>(&r);
-}
-#endif
-
 struct GemmProblem {
   int n_img;
   int m_tiles;   // ceil(rows_in / 128)

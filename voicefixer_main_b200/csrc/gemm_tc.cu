@@ -88,10 +88,8 @@ __device__ __forceinline__ void pack_hi_lo(const float (&v)[32], uint32_t (&hi)[
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    const float2 f = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
     hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    lo[i] = residual_h2(v[2 * i], v[2 * i + 1], hi[i]);      // one FHADD per element instead of a conversion and an FSUB
   }
 }
 
@@ -553,11 +551,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             const __half2* ph = reinterpret_cast<const __half2*>(&xh);
             const __half2* pl = reinterpret_cast<const __half2*>(&xl);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 fh = __half22float2(resid_ar ? ar_unact(ph[k], resid_ar) : ph[k]), fl = __half22float2(pl[k]);
-              v[8 * i + 2 * k] += fh.x + fl.x;
-              v[8 * i + 2 * k + 1] += fh.y + fl.y;
-            }
+            for (int k = 0; k < 4; ++k)
+              add_planes(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], reinterpret_cast<const uint32_t*>(ph)[k], reinterpret_cast<const uint32_t*>(pl)[k], resid_ar);
           }
           __syncwarp();
           issue_resid();                  // the slot just read is free again: request the chunk `resid_ring` ahead
@@ -592,11 +587,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
             const __half2* ph = reinterpret_cast<const __half2*>(&xh);
             const __half2* pl = reinterpret_cast<const __half2*>(&xl);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 fh = __half22float2(resid_ar ? ar_unact(ph[k], resid_ar) : ph[k]), fl = __half22float2(pl[k]);
-              v[8 * i + 2 * k] += fh.x + fl.x;
-              v[8 * i + 2 * k + 1] += fh.y + fl.y;
-            }
+            for (int k = 0; k < 4; ++k)
+              add_planes(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], reinterpret_cast<const uint32_t*>(ph)[k], reinterpret_cast<const uint32_t*>(pl)[k], resid_ar);
           }
         }
         const bool pad = (flags & kRowPad) != 0;

@@ -305,11 +305,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1) pair_tc_kernel(const __grid_c
             const __half2* ph2 = reinterpret_cast<const __half2*>(&yh);
             const __half2* pl2 = reinterpret_cast<const __half2*>(&yl);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 fh = __half22float2(AR ? ar_unact(ph2[k], ar_in) : ph2[k]), fl = __half22float2(pl2[k]);
-              v[8 * i + 2 * k] += fh.x + fl.x;
-              v[8 * i + 2 * k + 1] += fh.y + fl.y;
-            }
+            for (int k = 0; k < 4; ++k)
+              add_planes(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], reinterpret_cast<const uint32_t*>(ph2)[k], reinterpret_cast<const uint32_t*>(pl2)[k], AR ? ar_in : 0u);
           }
         }
         if (!AR) e2_bar_sync();                // the fp32 result overwrites the plane tiles other warps still read

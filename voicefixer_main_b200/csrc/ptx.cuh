@@ -171,6 +171,53 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 }
 
 // 32 lanes x 16 consecutive fp32 columns.
+// Mixed-precision adds (PTX ISA 8.6, sm_100+; SASS FHADD): fp16 + fp32 -> fp32 in ONE instruction, the half selected by a
+// register sub-word modifier - replaces a conversion plus an FADD wherever an epilogue mixes fp16 planes with fp32 values.
+__device__ __forceinline__ float add_f32_f16(const unsigned short h, const float c) {      // h + c
+  float d;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float sub_f32_f16(const unsigned short h, const float c) {      // h - c
+  float d;
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(h), "f"(c));
+  return d;
+}
+// v0 += lo half of w, v1 += hi half of w (w = a packed half2)
+__device__ __forceinline__ void add_h2(float& v0, float& v1, const uint32_t w) {
+  v0 = add_f32_f16((unsigned short)(w & 0xffffu), v0);
+  v1 = add_f32_f16((unsigned short)(w >> 16), v1);
+}
+// packed half2 of (v0 - h.x, v1 - h.y), h given as its bits: the "lo" word of a hi/lo split
+__device__ __forceinline__ uint32_t residual_h2(const float v0, const float v1, const uint32_t hbits) {
+  const float d0 = sub_f32_f16((unsigned short)(hbits & 0xffffu), v0), d1 = sub_f32_f16((unsigned short)(hbits >> 16), v1);   // h - v
+  const __half2 l = __floats2half2_rn(-d0, -d1);
+  return *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---- (a, r) residual stream (GemmEpilogue::resid_ar / out_ar in gemm.cuh)
+__device__ __forceinline__ __half2 ar_unact(const __half2 a, const uint32_t inv_bits) {
+  return __hmin2(a, __hmul2(a, *reinterpret_cast<const __half2*>(&inv_bits)));
+}
+// (a, r) of two values already activated to a0 = lrelu(v0), a1 = lrelu(v1)
+__device__ __forceinline__ void ar_split(const float v0, const float v1, const float a0, const float a1, const uint32_t inv_bits,
+                                         uint32_t& a_bits, uint32_t& r_bits) {
+  const __half2 a = __floats2half2_rn(a0, a1);
+  const __half2 u = ar_unact(a, inv_bits);
+  a_bits = *reinterpret_cast<const uint32_t*>(&a);
+  r_bits = residual_h2(v0, v1, *reinterpret_cast<const uint32_t*>(&u));
+}
+// v += x for two elements of a residual kept as planes: (hi, lo) of x, or (a, r) when inv_bits != 0
+__device__ __forceinline__ void add_planes(float& v0, float& v1, const uint32_t hbits, const uint32_t lbits, const uint32_t inv_bits) {
+  uint32_t h = hbits;
+  if (inv_bits) {
+    const __half2 u = ar_unact(*reinterpret_cast<const __half2*>(&hbits), inv_bits);
+    h = *reinterpret_cast<const uint32_t*>(&u);
+  }
+  add_h2(v0, v1, h);
+  add_h2(v0, v1, lbits);
+}
+
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
