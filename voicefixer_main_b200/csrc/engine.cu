@@ -595,6 +595,18 @@ struct Builder {
     if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(out planes: ld=%d rows=%d planes=%d) -> %d", ld, rows, planes, (int)r);
     return VF_OK;
   }
+  // activated planes of a transposed 1-D conv: output row t = s * q + p as [ld, p, q, image, plane], box 32 x 1 x 32 x 1 x planes
+  int make_map_ct5(CUtensorMap* m, const __half* hi, const __half* lo, int planes, int ld, int s, long L, int n_img) {
+    const size_t pstride = planes == 2 ? (size_t)(lo - hi) : (size_t)n_img * L * ld;
+    cuuint64_t dims[5] = {(cuuint64_t)ld, (cuuint64_t)s, (cuuint64_t)(L / s), (cuuint64_t)n_img, (cuuint64_t)planes};      // strides ascending
+    cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * s, (cuuint64_t)L * ld * 2, (cuuint64_t)pstride * 2};
+    cuuint32_t box[5] = {32, 1, 32, 1, (cuuint32_t)planes};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, VF_ECUDA, "cuTensorMapEncodeTiled(convT1d out: ld=%d s=%d L=%ld planes=%d) -> %d", ld, s, L, planes, (int)r);
+    return VF_OK;
+  }
   // 3-term operands: hi and lo planes in ONE box ([C, rows, image, plane] / [K, N, plane]) - half the TMA issues
   int make_map4(CUtensorMap* m, const __half* base, int C, int rows, int img_rows, int n_img, size_t plane_stride, int box_c, bool sw128, int box_rows) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_img, 2};
@@ -848,6 +860,12 @@ struct Builder {
           if (terms == 3 && pe.resid) rc = make_map3_any(&tp.i_res, pe.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pe.resid_ld, pe.rows_in, (size_t)pe.rows_in, n_img, 32, 32);
           else rc = make_map_out4(&tp.i_res, pe.resid_hi, pe.resid_lo, 2, pe.resid_ld, pe.rows_in, (size_t)pe.rows_in, n_img);
           if (rc) return;
+        }
+        if (pe.map == MAP_CONVT1D && (want & 4) && !ctx->validate_simt && pe.out_a.hi && !pe.out_r.hi && !pe.out_raw && pe.out_row0 == 0 &&
+            pe.out_rows_valid == pe.out_img_rows && pe.out_img_rows % pe.ct_stride == 0 && pe.out_a.ld % 8 == 0) {
+          rc = make_map_ct5(&tp.o_a, pe.out_a.hi, pe.out_a.lo, (terms == 3 || pe.out_ar) ? 2 : 1, pe.out_a.ld, pe.ct_stride, pe.out_img_rows, n_img);
+          if (rc) return;
+          pe.tma_out |= 8;
         }
         if (pe.map == MAP_PLAIN && want) {
           if ((want & 1) && terms == 3 && pe.out_raw && pe.raw_ld % 4 == 0) {

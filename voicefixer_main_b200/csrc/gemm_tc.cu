@@ -341,7 +341,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
     // 128-byte rows) / SWIZZLE_64B (fp16, 64-byte rows) expect - chunk ^ (row & 7) and chunk ^ ((row >> 1) & 3) are exactly the
     // SO_F / SO_H slots - so lane 0 hands a finished tile to the copy engine instead of the warp reading it back row-major and
     // storing it with 12 STG per lane: half the LSU wavefronts of the store path, which bounds the narrow layers (ncu l1tex 60-86 %)
-    const int tma_out = (map == MAP_PLAIN) ? e.tma_out : 0;
+    // (bit 3: the activated planes of a MAP_CONVT1D layer through a 5-D map [C, phase, q, image, plane] - output row
+    // stride * q + phase - the 32 rows of a warp are one box per column chunk)
+    const int tma_out = (map == MAP_PLAIN) ? (e.tma_out & 7) : (map == MAP_CONVT1D ? (e.tma_out & 8) : 0);
     bool st_pending = false;             // a TMA store of this warp may still be reading its staging tile (warp-uniform)
     auto stg_release = [&]() {
       if (st_pending) {
@@ -657,37 +659,65 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
           uint32_t hi[16], lo[16];
           if (out_ar) {                     // (a, r) stream: hi plane = fp16(lrelu(v)), lo plane = fp16(v - U(a)); |v| itself is range-checked
+            if (row_ok) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float v0 = pad ? 0.f : v[2 * i], v1 = pad ? 0.f : v[2 * i + 1];
-              ar_split(v0, v1, fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope), out_ar, hi[i], lo[i]);
+              for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
             }
-          } else if (act == ACT_LRELU) {    // slope in [0, 1]: max(a, slope * a)
+            stg_release();
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], v[i] * slope);
-          } else if (act == ACT_ELU) {
+            for (int i = 0; i < 4; ++i) {   // eight columns at a time straight into the staging tiles: no 32 packed words live at once
+              uint32_t h4[4], l4[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+              for (int k = 0; k < 4; ++k) {
+                const float v0 = pad ? 0.f : v[8 * i + 2 * k], v1 = pad ? 0.f : v[8 * i + 2 * k + 1];
+                ar_split(v0, v1, fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope), out_ar, h4[k], l4[k]);
+              }
+              stg_h[SO_H(i)] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+              stg_l[SO_H(i)] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+            }
+          } else {
+            if (act == ACT_LRELU) {           // slope in [0, 1]: max(a, slope * a)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], v[i] * slope);
+            } else if (act == ACT_ELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+            }
+            if (pad) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
+            }
+            if (THREE) pack_hi_lo(v, hi, lo); else pack_hi(v, hi);
+            stg_release();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              stg_h[SO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              if (THREE) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
           }
-          if (pad) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          }
-          if (row_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
-          }
-          if (THREE) pack_hi_lo(v, hi, lo);
-          else if (!out_ar) pack_hi(v, hi);
-          stg_release();
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            stg_h[SO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            if (THREE || out_ar) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          // A TMA store whose box STARTS at a negative coordinate faults (illegal instruction; tools/probe_tma5d.cu - boxes that
+          // run past the upper bound are clipped as documented): the one warp per image and early phase whose first output row
+          // would be q = -1 keeps the LDS + STG path.
+          if ((tma_out & 8) && !(wrow0 == 0 && nb / cout < e.ct_pad)) {      // t = stride * r + phase - pad = stride * (r - up) + (phase - pad + up * stride)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int d = nb / cout - e.ct_pad;
+              const int up = d < 0 ? 1 : 0;
+              tma_store_5d(&P.o_a, stg_h, e.out_a.c_off + co0, d + up * e.ct_stride, wrow0 - up, img, 0);
+              tma_store_commit();
+            }
+            st_pending = true;
+          } else {
+            store_rows_h(e.out_a, co0, THREE || out_ar, (tma_out & 4) ? &P.o_a : nullptr);
           }
-          __syncwarp();
-          store_rows_h(e.out_a, co0, THREE || out_ar, (tma_out & 4) ? &P.o_a : nullptr);
         }
       };
 
