@@ -93,6 +93,21 @@ __device__ __forceinline__ void pack_hi_lo(const float (&v)[32], uint32_t (&hi)[
   }
 }
 
+// Eight columns (v[8 i .. 8 i + 7]) -> one 16-byte word of the hi plane (and of the lo plane): packing straight into the
+// staging tiles keeps 8 instead of 32 packed words live - the two- and three-CTA variants have no registers to spare.
+template <bool TWO>
+__device__ __forceinline__ void pack8(const float (&v)[32], const int i, uint4& h, uint4& l) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half2 h2 = __floats2half2_rn(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]);
+    hw[k] = *reinterpret_cast<const uint32_t*>(&h2);
+    if (TWO) lw[k] = residual_h2(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], hw[k]);
+  }
+  h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  if (TWO) l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
 // The MMAs of one K chunk: G taps (row shifts packed 2 bits each in `shifts`) x BK/16 K steps; 3-term mode adds
 // lo(A) x hi(B) into the correction half, BOTH (hi-only identity tap) contracts the lo plane into the same accumulator.
 template <int BN, int BK, bool THREE, int G, bool BOTH>
@@ -630,14 +645,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           }
         }
         if (want_r) {                     // raw hi/lo planes
-          uint32_t hi[16], lo[16];
-          pack_hi_lo(v, hi, lo);
           stg_release();
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            stg_h[SO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            uint4 h, l;
+            pack8<true>(v, i, h, l);
+            stg_h[SO_H(i)] = h;
+            stg_l[SO_H(i)] = l;
           }
           __syncwarp();
           store_rows_h(e.out_r, co0, true, (tma_out & 2) ? &P.o_r : nullptr);
@@ -657,7 +672,6 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
               v[4 * i + 2] = fmaf(v[4 * i + 2], a4.z, b4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], a4.w, b4.w);
             }
           }
-          uint32_t hi[16], lo[16];
           if (out_ar) {                     // (a, r) stream: hi plane = fp16(lrelu(v)), lo plane = fp16(v - U(a)); |v| itself is range-checked
             if (row_ok) {
 #pragma unroll
@@ -692,13 +706,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
 #pragma unroll
               for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
             }
-            if (THREE) pack_hi_lo(v, hi, lo); else pack_hi(v, hi);
             stg_release();
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              stg_h[SO_H(i)] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              if (THREE) stg_l[SO_H(i)] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              uint4 h, l;
+              pack8<THREE>(v, i, h, l);
+              stg_h[SO_H(i)] = h;
+              if (THREE) stg_l[SO_H(i)] = l;
             }
           }
           __syncwarp();
@@ -733,15 +748,31 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, MINB)
           for (int jj = 0; jj < NJ; ++jj) {
             const int j = half + jj * CHUNK_STEP;
             if (j < BN / 32) {
-              float w[32], c[32];
-              tmem_ld_32x32(tmem_base + lane_bits + buf * 2 * BN + j * 32, w);
-              tmem_ld_32x32(tmem_base + lane_bits + buf * 2 * BN + BN + j * 32, c);
-              if (sg == 0) {
+              if constexpr (MINB >= 2) {      // register-capped variants: 16 columns of both accumulators at a time
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[jj][i] = w[i] + c[i];
+                for (int hh = 0; hh < 2; ++hh) {
+                  float w[16], c[16];
+                  const uint32_t ta = tmem_base + lane_bits + buf * 2 * BN + j * 32 + hh * 16;
+                  tmem_ld2_32x16(ta, ta + BN, w, c);
+                  if (sg == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[jj][hh * 16 + i] = w[i] + c[i];
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[jj][hh * 16 + i] += w[i] + c[i];
+                  }
+                }
               } else {
+                float w[32], c[32];
+                tmem_ld_32x32(tmem_base + lane_bits + buf * 2 * BN + j * 32, w);
+                tmem_ld_32x32(tmem_base + lane_bits + buf * 2 * BN + BN + j * 32, c);
+                if (sg == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[jj][i] += w[i] + c[i];
+                  for (int i = 0; i < 32; ++i) acc[jj][i] = w[i] + c[i];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) acc[jj][i] += w[i] + c[i];
+                }
               }
             }
           }
