@@ -152,3 +152,26 @@ def test_pip_entry_points_refuse_what_is_not_built():
         m.restore("in.wav", "out.wav", cuda=False, mode=0)
     with pytest.raises(RuntimeError):                        # not on a device yet
         m.restore("in.wav", "out.wav")
+
+
+def test_ar_residual_stream_arithmetic_keeps_22_bits():
+    """the hi-only vocoder keeps its residual stream as a = fp16(lrelu_s(x)) and r = fp16(x - U(a)),
+    U(a) = min(a, a * fp16(1/s)) evaluated in fp16 (csrc/ptx.cuh ar_unact / ar_split).  Restated in numpy: U(a) + r recovers
+    x to ~2^-21 relative - the precision of a hi/lo split of x itself - for every slope the engine accepts."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.standard_normal(200000) * 3.0, rng.standard_normal(1000) * 1e-4, [0.0, -0.0, 65000.0, -65000.0]]).astype(np.float32)
+    for s in (0.1, 0.2, 0.01, 1.0):
+        inv = np.float16(1.0 / s)
+        a = np.maximum(x, x * np.float32(s)).astype(np.float16)                      # fmaxf(v, v * slope) -> fp16
+        with np.errstate(over="ignore"):                                              # a * inv may overflow to +inf: min() keeps a
+            u = np.minimum(a, (a * inv).astype(np.float16))                          # __hmin2(a, __hmul2(a, inv))
+        r = (x - u.astype(np.float32)).astype(np.float16)                            # FHADD + pack
+        back = u.astype(np.float32) + r.astype(np.float32)
+        hi = x.astype(np.float16)
+        lo = (x - hi.astype(np.float32)).astype(np.float16)
+        err_ar = np.abs(back - x)
+        err_hl = np.abs(hi.astype(np.float32) + lo.astype(np.float32) - x)
+        bound = np.abs(x) * 2.0 ** -20 + 2.0 ** -24                                  # fp16 subnormal floor for tiny values
+        assert np.all(np.isfinite(back)) and np.all(err_ar <= bound), (s, float((err_ar / np.maximum(np.abs(x), 1e-30)).max()))
+        assert float(err_ar.max()) <= 4.0 * float(err_hl.max()) + 2.0 ** -24
