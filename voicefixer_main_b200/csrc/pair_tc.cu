@@ -2,8 +2,9 @@
 //     x_new = x + conv_b(lrelu(conv_a(lrelu(x)) + bias_a)) + bias_b          (oracle: vocoder_generator, the `res.s.i` pair)
 // conv_a: k = 3, dilation d, zero padding;  conv_b: k = 3, dilation 1, zero padding.  hi-only fp16 operands, fp32
 // accumulation (the vocoder's 1-term mode).  What two separate GEMM launches move through HBM in between - the activated
-// intermediate h, written by "a" and read back by "b" (4 of 16 bytes per element) - stays in shared memory, and the
-// residual stream of a fused stack is fp32 (same 4 bytes per element as the hi/lo planes, no split arithmetic).
+// intermediate h, written by "a" and read back by "b" (4 of 16 bytes per element) - stays in shared memory.  The residual
+// stream of a fused stack is the (a, r) pair of gemm.cuh by default (MODE 2: 8 bytes per element), or fp32 (MODE 0 / 1:
+// 12 bytes per element, VF_TUNE_AR_STREAM=0).
 //
 //   tile = 126 output rows t0 .. t0+125 of one clip, m0 = t0 - 1.
 //   P1 (conv_a)   A = lrelu(x) rows m0 + (tap-1) d + [0,128) by TMA (out-of-range rows zero filled), accumulator 1 = h rows
@@ -24,6 +25,12 @@
 //   STS/LDS of its row-per-thread <-> row-major staging transposes, is the limiter (DRAM at 58-65 %).  Hence this version:
 //   r2d  the residual tile arrives by TMA (SWIZZLE_128B, read conflict-free by the row's own thread), x_new is written
 //        back IN PLACE and leaves by TMA store, as does the activated tile: no LDG / STG, no staging transposes.
+//
+//   r2e  three residual stages re-armed by the store warp, readiness-driven MMA issue order                 1.87   (10.9 GB = 12 B/element
+//        at 5.8-6.0 TB/s: HBM-bound, only fewer bytes help)
+//   r2f  MODE 2, the (a, r) stream of gemm.cuh: the residual is rebuilt from the activated plane (its TMA re-read is an L2 hit -
+//        the centre tap has just fetched those rows) plus an fp16 correction plane, and x_new leaves as the same pair:
+//        8 B/element, 1.51-1.58 ms per pair; the output warps' instruction stream is the limit now (FHADD adds, ptx.cuh)
 //
 // Warp roles (every wait is bounded, ptx.cuh):
 //   warp 0       TMA producer: ring of three A tap slots (16 KB each); both weight matrices (2 x 3 x 8 KB) are loaded once and
