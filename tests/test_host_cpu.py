@@ -175,3 +175,29 @@ def test_ar_residual_stream_arithmetic_keeps_22_bits():
         bound = np.abs(x) * 2.0 ** -20 + 2.0 ** -24                                  # fp16 subnormal floor for tiny values
         assert np.all(np.isfinite(back)) and np.all(err_ar <= bound), (s, float((err_ar / np.maximum(np.abs(x), 1e-30)).max()))
         assert float(err_ar.max()) <= 4.0 * float(err_hl.max()) + 2.0 ** -24
+
+
+def test_restore_inmem_segmentation_with_a_stub_model(tmp_path):
+    """handler.restore_inmem: all whole 30 s segments go through ONE batched call, the ragged tail through a second, and
+    the pieces come back in order (host logic only: the model is a stub that scales its input)."""
+    import numpy as np
+    from voicefixer_main_b200 import handler as H
+
+    class Stub:
+        device = torch.device("cpu")
+        calls = []
+
+        def restore(self, x, unify_energy=False):
+            self.calls.append((tuple(x.shape), unify_energy))
+            return x * 0.5
+
+    seg = H.PIP_SEG_LENGTH
+    for n in (seg // 3, seg, 2 * seg + 777):
+        m = Stub()
+        m.calls = []
+        wav = np.arange(n, dtype=np.float32) / n
+        out = H.restore_inmem(m, wav, cuda=True, mode=0)
+        assert out.shape == (1, n) and np.array_equal(out[0], wav * 0.5)
+        want = ([((n // seg, seg), True)] if n >= seg else []) + ([((1, n % seg), True)] if n % seg else [])
+        assert m.calls == want
+    assert H.restore_inmem(Stub(), np.zeros(0, np.float32)).shape == (1, 0)
